@@ -1,0 +1,175 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz (inputs + reference outputs, a few hundred KB in total).  The reference
+is imported read-only (no bytecode is written); ``fno/data_gen/solvers.py`` is loaded by file path
+with ``tqdm`` injected (it forgets to import it), and the packages with
+import-time side effects (fno.pipeline, fno.utils, fno.data_gen) are never imported.
+"""
+import importlib.util
+import os
+import sys
+
+sys.dont_write_bytecode = True
+REF = os.environ.get("TORCH_CFD_REF", "/root/reference")
+sys.path.insert(0, REF)
+
+import numpy as np
+import torch
+import torch.fft as fft
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def load_solvers():
+    spec = importlib.util.spec_from_file_location(
+        "ref_solvers", os.path.join(REF, "fno", "data_gen", "solvers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from tqdm import tqdm
+    mod.tqdm = tqdm
+    return mod
+
+
+def ns2d_case(name, n, batch, dtype, viscosity, drag, forcing, steps_list, dt=1e-3, low_storage=True,
+              traj=None, diam=2 * torch.pi):
+    """forcing: None | 'vorticity' | 'velocity'."""
+    torch.set_default_dtype(dtype)
+    from torch_cfd.grids import Grid
+    from torch_cfd.equations import NavierStokes2DSpectral, RK4CrankNicolsonStepper
+    from torch_cfd.forcings import KolmogorovForcing
+    from torch_cfd.initial_conditions import vorticity_field
+
+    grid = Grid(shape=(n, n), domain=((0, diam), (0, diam)))
+    if forcing is None:
+        forcing_fn = None
+    else:
+        # k=4 is swallowed by **kwargs upstream: effective wave number 1
+        forcing_fn = KolmogorovForcing(diam=diam, wave_number=1, grid=grid, k=4, scale=1,
+                                       vorticity=(forcing == "vorticity"))
+    ns = NavierStokes2DSpectral(viscosity=viscosity, grid=grid, drag=drag, smooth=True,
+                                forcing_fn=forcing_fn,
+                                solver=RK4CrankNicolsonStepper(low_storage=low_storage))
+    w0 = torch.stack([vorticity_field(grid, 4, random_state=s).data for s in range(batch)])
+    w0_hat = fft.rfft2(w0)
+    if batch == 1 and name.endswith("nobatch"):
+        w0_hat = w0_hat[0]
+    out = dict(n=n, batch=batch, dt=dt, viscosity=viscosity, drag=drag, diam=float(diam),
+               forcing=str(forcing), low_storage=int(low_storage),
+               kx=_np(ns.kx), ky=_np(ns.ky), laplace=_np(ns.laplace),
+               linear_term=_np(ns.linear_term), filter=_np(ns.filter),
+               w0_hat=_np(w0_hat))
+    with torch.no_grad():
+        out["F0"] = _np(ns.explicit_terms(w0_hat))
+        out["G0"] = _np(ns.implicit_terms(w0_hat))
+        out["solve0"] = _np(ns.implicit_solve(w0_hat, 0.5 * dt))
+        for s in steps_list:
+            w, dwdt = ns(w0_hat, dt, steps=s)
+            out[f"w_{s}"] = _np(w)
+            out[f"dwdt_{s}"] = _np(dwdt)
+        out["res_1"] = _np(ns.residual(torch.from_numpy(out["w_1"]), torch.from_numpy(out["dwdt_1"])))
+        if traj is not None:
+            solvers = load_solvers()
+            num_steps, every = traj
+            res = solvers.get_trajectory_imex(ns, w0_hat, dt, num_steps=num_steps,
+                                              record_every_steps=every, pbar=False)
+            for k, v in res.items():
+                out[f"traj_{k}"] = _np(v)
+            out["traj_num_steps"] = num_steps
+            out["traj_every"] = every
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(name, {k: getattr(v, "shape", v) for k, v in out.items() if k.startswith("w_")})
+
+
+def mask_case():
+    torch.set_default_dtype(torch.float32)
+    from torch_cfd.grids import Grid
+    from torch_cfd.spectral import brick_wall_filter_2d
+    out = {}
+    for n in [16, 32, 64, 128, 256, 512, 1024, 2048]:
+        m = brick_wall_filter_2d(Grid(shape=(n, n), domain=((0, 1), (0, 1))))
+        rows = (m.sum(1) > 0).nonzero().flatten()
+        cols = (m.sum(0) > 0).nonzero().flatten()
+        r_lo = int((rows < n // 2).sum())
+        r_hi = int((rows >= n // 2).sum())
+        out[f"n{n}"] = np.array([r_lo, r_hi, len(cols), int(m.sum())])
+        if n <= 64:
+            out[f"mask{n}"] = _np(m).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "mask_bounds.npz"), **out)
+    print("mask", {k: v.tolist() for k, v in out.items() if k.startswith("n")})
+
+
+def sconv_cases():
+    torch.set_default_dtype(torch.float32)
+    from fno.fno3d import SpectralConv3d
+    from fno.sfno import SpectralConvS, SpectralConvT
+    out = {}
+
+    def run(tag, mod, x, **fw):
+        x = x.clone().requires_grad_(True)
+        y = mod(x, **fw)
+        g = torch.Generator().manual_seed(123)
+        cot = torch.randn(y.shape, generator=g)
+        (y * cot).sum().backward()
+        out[f"{tag}_x"] = _np(x)
+        out[f"{tag}_y"] = _np(y)
+        out[f"{tag}_cot"] = _np(cot)
+        out[f"{tag}_gx"] = _np(x.grad)
+        for pname, p in mod.named_parameters():
+            key = pname.replace(".", "_")
+            out[f"{tag}_p_{key}"] = _np(torch.view_as_real(p) if p.is_complex() else p)
+            gp = p.grad
+            out[f"{tag}_g_{key}"] = _np(torch.view_as_real(gp) if gp.is_complex() else gp)
+        print(tag, tuple(x.shape), "->", tuple(y.shape))
+
+    torch.manual_seed(0)
+    # SpectralConv3d: (b, C, X, Y, T)
+    m = SpectralConv3d(3, 4, 4, 3, 3)
+    run("c3d_a", m, torch.randn(2, 3, 16, 8, 6))
+    m = SpectralConv3d(2, 2, 5, 5, 4)
+    run("c3d_b", m, torch.randn(1, 2, 16, 16, 10))
+    # SpectralConvS (real (..,2) weights), no bias
+    m = SpectralConvS(3, 2, 4, 4, 3)
+    run("cs_a", m, torch.randn(2, 3, 8, 16, 8))
+    # SpectralConvS with bias (bias is zero-initialised upstream: randomise it so it is exercised)
+    m = SpectralConvS(2, 3, 3, 4, 2, bias=True, delta=0.5)
+    with torch.no_grad():
+        for b in m.bias:
+            b.copy_(torch.randn_like(b))
+    run("cs_bias", m, torch.randn(2, 2, 8, 8, 6))
+    # SpectralConvS with a different output mesh
+    m = SpectralConvS(2, 2, 3, 3, 3)
+    run("cs_outmesh", m, torch.randn(1, 2, 8, 8, 8), out_mesh_size=[16, 16, 12])
+    # SpectralConvT: temporal padding + out_steps != in steps, bias on
+    m = SpectralConvT(2, 2, 4, 4, 5, out_steps=12, temporal_padding=True, bias=True)
+    with torch.no_grad():
+        for b in m.bias:
+            b.copy_(torch.randn_like(b))
+    run("ct_pad", m, torch.randn(2, 2, 8, 8, 10))
+    # SpectralConvT: no padding, explicit out_steps at call time
+    m = SpectralConvT(3, 2, 3, 3, 3, bias=True, temporal_padding=False)
+    run("ct_nopad", m, torch.randn(1, 3, 8, 16, 8), out_steps=5)
+    np.savez_compressed(os.path.join(HERE, "sconv.npz"), **out)
+
+
+if __name__ == "__main__":
+    # C1 (BASELINE.json configs[0]): 64^2, batch 1, fp64, Kolmogorov vorticity forcing, drag 0.1
+    ns2d_case("ns2d_c1_fp64", 64, 1, torch.float64, 1e-3, 0.1, "vorticity", [1, 2, 100], traj=(6, 2))
+    # C2-like small: fp32, batch 3, unforced, no drag
+    ns2d_case("ns2d_fp32_unforced", 64, 3, torch.float32, 1e-3, 0.0, None, [1, 10, 50])
+    # velocity-form forcing (data_gen_Kolmogorov2d.py form), fp64, n=32
+    ns2d_case("ns2d_fp64_velforce", 32, 2, torch.float64, 1e-3, 0.1, "velocity", [1, 20])
+    # (low_storage=False cannot be generated: upstream builds an integer `betas` tensor and
+    #  nn.Parameter rejects it -- RuntimeError at torch_cfd/equations.py:326,167.)
+    # un-batched (n, nh) input, n=128, fp32
+    ns2d_case("ns2d_fp32_n128_nobatch", 128, 1, torch.float32, 1e-3, 0.1, "vorticity", [1, 5],
+              traj=(4, 1))
+    mask_case()
+    sconv_cases()
