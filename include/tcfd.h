@@ -1,0 +1,103 @@
+/* tcfd.h -- C ABI of the B200-native torch-cfd spectral hot path (libtcfd.so).
+ *
+ * The reference (scaomath/torch-cfd) is pure Python and has no FFI seam for this path: the
+ * seam is its nn.Module API.  Each entry point below therefore names the reference *method* it
+ * stands behind; the Python shims in torch-cfd_b200/ keep those methods' names and signatures and
+ * forward to these functions through ctypes (see INTEGRATION.md for the binding a maintainer
+ * would add upstream).
+ *
+ * Conventions
+ *  - Plain C: pointers + sizes only, no torch types.  Device pointers are raw CUDA addresses
+ *    (torch: tensor.data_ptr()); the library never frees or reallocates caller memory.
+ *  - Complex arrays are interleaved (re, im) pairs of float (prec 32) or double (prec 64), in
+ *    the reference's layout: spectrum (B, n, n/2+1) row-major, "backward" normalisation.
+ *  - All kernels are enqueued on the caller's stream (cudaStream_t passed as void*); calls are
+ *    asynchronous with respect to the host and never synchronise.
+ *  - Every function returns 0 on success or a negative tcfd error code; tcfd_last_error()
+ *    returns a thread-local human-readable message.  Nothing throws or exits.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TCFD_H_
+#define TCFD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCFD_OK 0
+#define TCFD_ERR_INVALID (-1) /* bad argument / unsupported size */
+#define TCFD_ERR_CUDA (-2)    /* a CUDA runtime call failed */
+#define TCFD_ERR_NOMEM (-3)
+
+const char* tcfd_last_error(void);
+/* library version / build string, e.g. "tcfd 0.1 sm_100a" */
+const char* tcfd_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path A: pseudo-spectral 2-D vorticity Navier-Stokes, RK4 (Carpenter-Kennedy) + CN.
+ * Replaces: NavierStokes2DSpectral (torch_cfd/equations.py:361-463) driven by
+ *           RK4CrankNicolsonStepper.forward (torch_cfd/equations.py:328-358).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tcfd_ns2d tcfd_ns2d_t;
+
+typedef struct {
+  int n;         /* grid is n x n, n a power of two in [32, 2048] */
+  int prec;      /* 32 or 64: precision of every table and of the state */
+  int max_batch; /* workspace is sized for this many samples */
+  /* HOST pointers, copied at creation.  They are the reference's own buffers
+   * (NavierStokes2DSpectral._initialize, torch_cfd/equations.py:394-403), so that rounding of the
+   * tables is the reference's, not ours: */
+  const void* kappa_x;     /* [n]        imag(2j*pi*kx[:,0])   (torch_cfd/equations.py:417)        */
+  const void* kappa_y;     /* [n/2+1]    imag(2j*pi*ky[0,:])                                        */
+  const void* neg_inv_lap; /* [n][n/2+1] -1/laplace' with laplace'[0,0]=1 (torch_cfd/spectral.py:41-46,113) */
+  const void* linear_term; /* [n][n/2+1] viscosity*laplace - drag       (torch_cfd/equations.py:401)*/
+  const void* filter;      /* [n][n/2+1] 2/3 brick-wall mask, or NULL when smooth=False
+                              (torch_cfd/spectral.py:78-84, torch_cfd/equations.py:424-425)         */
+  const void* f_hat;       /* [n][n/2+1] complex forcing spectrum added to F, or NULL
+                              (torch_cfd/equations.py:429-437)                                      */
+} tcfd_ns2d_desc_t;
+
+int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* desc);
+int tcfd_ns2d_destroy(tcfd_ns2d_t* h);
+/* replace the forcing spectrum (HOST pointer, NULL = no forcing) */
+int tcfd_ns2d_set_forcing(tcfd_ns2d_t* h, const void* f_hat);
+/* bytes of device workspace owned by the handle */
+size_t tcfd_ns2d_workspace_bytes(const tcfd_ns2d_t* h);
+/* number of kernel launches the last tcfd_ns2d_* compute call enqueued */
+int tcfd_ns2d_last_launch_count(const tcfd_ns2d_t* h);
+
+/* NavierStokes2DSpectral.forward(vort_hat, dt, steps) with an RK4CrankNicolsonStepper
+ * (torch_cfd/equations.py:452-463, :328-358).
+ *   w_in   [batch][n][n/2+1] complex, device, read-only
+ *   w_out  same shape, device, must not alias w_in
+ *   dwdt   same shape or NULL: (w_out - w_in) * inv_total_dt     (equations.py:462)
+ *   nstages, beta[nstages], gdt[nstages] = gammas[k]*dt, mu[nstages] = 0.5*dt*(alphas[k+1]-alphas[k]):
+ *          the stepper's coefficients, evaluated by the caller in the stepper's dtype exactly as
+ *          equations.py:355-357 does, passed as doubles.
+ */
+int tcfd_ns2d_step(tcfd_ns2d_t* h, const void* w_in, void* w_out, void* dwdt, int batch, int steps,
+                   int nstages, const double* beta, const double* gdt, const double* mu,
+                   double inv_total_dt, void* stream);
+
+/* NavierStokes2DSpectral.explicit_terms(vort_hat)  (torch_cfd/equations.py:413-441) */
+int tcfd_ns2d_explicit_terms(tcfd_ns2d_t* h, const void* w_in, void* f_out, int batch, void* stream);
+
+/* NavierStokes2DSpectral.residual(vhat, vt_hat) = vt_hat - F(vhat) - L vhat
+ * (torch_cfd/equations.py:405-411) */
+int tcfd_ns2d_residual(tcfd_ns2d_t* h, const void* w_in, const void* wt_in, void* r_out, int batch,
+                       void* stream);
+
+/* Same as tcfd_ns2d_step but with HOST buffers (pinned memory recommended): uploads w_in,
+ * steps, downloads w_out (and dwdt if not NULL) on `stream`, batch-chunked so copies overlap
+ * compute.  This is the end-to-end call a host-resident caller makes. */
+int tcfd_ns2d_step_host(tcfd_ns2d_t* h, const void* w_in_host, void* w_out_host, void* dwdt_host,
+                        int batch, int steps, int nstages, const double* beta, const double* gdt,
+                        const double* mu, double inv_total_dt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCFD_H_ */

@@ -1,0 +1,174 @@
+"""ctypes binding of the C ABI in include/tcfd.h (libtcfd.so, hand-written sm_100a kernels).
+
+PyTorch tensors cross this boundary only as raw device pointers (``tensor.data_ptr()``) plus
+sizes; the current CUDA stream is passed as an integer handle.  There is no CPU fallback: if the
+shared library is missing or no CUDA device is usable, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libtcfd.so")
+
+
+class _Desc(ctypes.Structure):
+    _fields_ = [
+        ("n", ctypes.c_int),
+        ("prec", ctypes.c_int),
+        ("max_batch", ctypes.c_int),
+        ("kappa_x", ctypes.c_void_p),
+        ("kappa_y", ctypes.c_void_p),
+        ("neg_inv_lap", ctypes.c_void_p),
+        ("linear_term", ctypes.c_void_p),
+        ("filter", ctypes.c_void_p),
+        ("f_hat", ctypes.c_void_p),
+    ]
+
+
+class TcfdLibrary:
+    """A loaded libtcfd with typed entry points."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"torch-cfd_b200: CUDA library not found at {path}. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C torch-cfd_b200/csrc`. "
+                "There is no CPU fallback."
+            )
+        self.path = path
+        self.c = ctypes.CDLL(path)
+        c = self.c
+        vp, ci, dp = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double)
+        c.tcfd_last_error.restype = ctypes.c_char_p
+        c.tcfd_version.restype = ctypes.c_char_p
+        c.tcfd_ns2d_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_Desc)]
+        c.tcfd_ns2d_destroy.argtypes = [vp]
+        c.tcfd_ns2d_set_forcing.argtypes = [vp, vp]
+        c.tcfd_ns2d_workspace_bytes.argtypes = [vp]
+        c.tcfd_ns2d_workspace_bytes.restype = ctypes.c_size_t
+        c.tcfd_ns2d_last_launch_count.argtypes = [vp]
+        c.tcfd_ns2d_step.argtypes = [vp, vp, vp, vp, ci, ci, ci, dp, dp, dp, ctypes.c_double, vp]
+        c.tcfd_ns2d_step_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, dp, dp, dp, ctypes.c_double, vp]
+        c.tcfd_ns2d_explicit_terms.argtypes = [vp, vp, vp, ci, vp]
+        c.tcfd_ns2d_residual.argtypes = [vp, vp, vp, vp, ci, vp]
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.c.tcfd_last_error().decode("utf-8", "replace")
+            raise RuntimeError(f"torch-cfd_b200: {what} failed ({rc}): {msg}")
+
+    def version(self) -> str:
+        return self.c.tcfd_version().decode()
+
+
+_LIB: Optional[TcfdLibrary] = None
+
+
+def load_library() -> TcfdLibrary:
+    """The product library.  Raises loudly when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        _LIB = TcfdLibrary(_LIB_PATH)
+    return _LIB
+
+
+def _darr(vals: Sequence[float]):
+    return (ctypes.c_double * len(vals))(*[float(v) for v in vals])
+
+
+def _stream_handle(t: torch.Tensor) -> int:
+    if t.is_cuda:
+        return torch.cuda.current_stream(t.device).cuda_stream
+    return 0
+
+
+class NS2DPlan:
+    """Owns one ``tcfd_ns2d_t`` handle: tables + workspace for (n, precision, max_batch) on the
+    current device.  Host tensors in, raw pointers out."""
+
+    def __init__(self, lib: TcfdLibrary, n: int, dtype: torch.dtype, max_batch: int,
+                 kappa_x: torch.Tensor, kappa_y: torch.Tensor, neg_inv_lap: torch.Tensor,
+                 linear_term: torch.Tensor, filter: Optional[torch.Tensor], f_hat: Optional[torch.Tensor]):
+        assert dtype in (torch.float32, torch.float64)
+        self.lib, self.n, self.nh, self.dtype, self.max_batch = lib, n, n // 2 + 1, dtype, max_batch
+        self.cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
+        self._h = ctypes.c_void_p()
+
+        def host(t, dt, shape):
+            t = t.detach().to("cpu", dt).contiguous()
+            assert tuple(t.shape) == tuple(shape), (tuple(t.shape), shape)
+            return t
+
+        keep = [host(kappa_x, dtype, (n,)), host(kappa_y, dtype, (self.nh,)),
+                host(neg_inv_lap, dtype, (n, self.nh)), host(linear_term, dtype, (n, self.nh))]
+        filt = None if filter is None else host(filter, dtype, (n, self.nh))
+        fh = None if f_hat is None else host(f_hat, self.cdtype, (n, self.nh))
+        d = _Desc(n, 32 if dtype == torch.float32 else 64, max_batch,
+                  keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr(),
+                  None if filt is None else filt.data_ptr(), None if fh is None else fh.data_ptr())
+        lib.check(lib.c.tcfd_ns2d_create(ctypes.byref(self._h), ctypes.byref(d)), "tcfd_ns2d_create")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.c.tcfd_ns2d_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.c.tcfd_ns2d_workspace_bytes(self._h))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.c.tcfd_ns2d_last_launch_count(self._h))
+
+    def set_forcing(self, f_hat: Optional[torch.Tensor]):
+        if f_hat is None:
+            self.lib.check(self.lib.c.tcfd_ns2d_set_forcing(self._h, None), "tcfd_ns2d_set_forcing")
+            return
+        fh = f_hat.detach().to("cpu", self.cdtype).contiguous()
+        assert tuple(fh.shape) == (self.n, self.nh)
+        self.lib.check(self.lib.c.tcfd_ns2d_set_forcing(self._h, fh.data_ptr()), "tcfd_ns2d_set_forcing")
+
+    def _check_state(self, t: torch.Tensor, name: str):
+        if t.dtype != self.cdtype or not t.is_contiguous() or t.dim() != 3 or tuple(t.shape[1:]) != (self.n, self.nh):
+            raise ValueError(f"{name}: expected contiguous {self.cdtype} tensor (B, {self.n}, {self.nh}), "
+                             f"got {t.dtype} {tuple(t.shape)} contiguous={t.is_contiguous()}")
+
+    def step(self, w_in: torch.Tensor, w_out: torch.Tensor, dwdt: Optional[torch.Tensor], steps: int,
+             beta: Sequence[float], gdt: Sequence[float], mu: Sequence[float], inv_total_dt: float,
+             host: bool = False):
+        self._check_state(w_in, "w_in")
+        self._check_state(w_out, "w_out")
+        if dwdt is not None:
+            self._check_state(dwdt, "dwdt")
+        fn = self.lib.c.tcfd_ns2d_step_host if host else self.lib.c.tcfd_ns2d_step
+        stream = torch.cuda.current_stream().cuda_stream if host and torch.cuda.is_available() else _stream_handle(w_in)
+        rc = fn(self._h, w_in.data_ptr(), w_out.data_ptr(), None if dwdt is None else dwdt.data_ptr(),
+                w_in.shape[0], int(steps), len(beta), _darr(beta), _darr(gdt), _darr(mu),
+                float(inv_total_dt), stream)
+        self.lib.check(rc, "tcfd_ns2d_step")
+
+    def explicit_terms(self, w_in: torch.Tensor, out: torch.Tensor):
+        self._check_state(w_in, "w_in")
+        self._check_state(out, "out")
+        self.lib.check(self.lib.c.tcfd_ns2d_explicit_terms(self._h, w_in.data_ptr(), out.data_ptr(),
+                                                           w_in.shape[0], _stream_handle(w_in)),
+                       "tcfd_ns2d_explicit_terms")
+
+    def residual(self, w_in: torch.Tensor, wt_in: torch.Tensor, out: torch.Tensor):
+        for t, nm in ((w_in, "w_in"), (wt_in, "wt_in"), (out, "out")):
+            self._check_state(t, nm)
+        self.lib.check(self.lib.c.tcfd_ns2d_residual(self._h, w_in.data_ptr(), wt_in.data_ptr(), out.data_ptr(),
+                                                     w_in.shape[0], _stream_handle(w_in)),
+                       "tcfd_ns2d_residual")

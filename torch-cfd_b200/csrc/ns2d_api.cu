@@ -1,0 +1,332 @@
+// C ABI of hot path A (see include/tcfd.h).  Host-side driver: owns tables, workspaces and the
+// launch sequence of one RK4+CN step; the arithmetic lives in ns2d_kernels.cuh.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tcfd.h"
+#include "ns2d_kernels.cuh"
+#include "ns2d_plan.h"
+
+#define TCFD_DECL(prec, n) extern "C" void tcfd_ns2d_entry_##prec##_##n(tcfd_ns2d_entry_t*);
+#define TCFD_SIZES(X, prec) X(prec, 32) X(prec, 64) X(prec, 128) X(prec, 256) X(prec, 512) X(prec, 1024) X(prec, 2048)
+TCFD_SIZES(TCFD_DECL, 32)
+TCFD_SIZES(TCFD_DECL, 64)
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(TCFD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+
+bool find_entry(int prec, int n, tcfd_ns2d_entry_t* e) {
+#define TCFD_TRY(p, nn)                                      \
+  if (prec == p && n == nn) {                                \
+    tcfd_ns2d_entry_##p##_##nn(e);                           \
+    return true;                                             \
+  }
+  TCFD_SIZES(TCFD_TRY, 32)
+  TCFD_SIZES(TCFD_TRY, 64)
+  return false;
+}
+}  // namespace
+
+struct tcfd_ns2d {
+  int n = 0, nh = 0, prec = 0, max_batch = 0, KF = 0, num_sms = 1;
+  size_t es = 0;  // sizeof(real)
+  tcfd_ns2d_entry_t entry{};
+  void *tw = nullptr, *kappa_x = nullptr, *kappa_y = nullptr, *nil = nullptr, *lin = nullptr,
+       *filt = nullptr, *fhat = nullptr;
+  void *hA = nullptr, *hB = nullptr, *wS = nullptr, *H = nullptr, *advt = nullptr;
+  void *stage_in = nullptr, *stage_out = nullptr, *stage_dw = nullptr;  // step_host staging
+  size_t ws_bytes = 0;
+  int launches = 0;
+  size_t state_bytes(int b) const { return (size_t)b * n * nh * 2 * es; }
+};
+
+extern "C" const char* tcfd_last_error(void) { return g_err.c_str(); }
+extern "C" const char* tcfd_version(void) {
+#ifdef TCFD_EMU
+  return "tcfd 0.1 host-emulation (tests only)";
+#else
+  return "tcfd 0.1 sm_100a";
+#endif
+}
+
+namespace {
+template <class T>
+int upload(void** dst, const void* src, size_t count) {
+  CUDA_TRY(cudaMalloc(dst, count * sizeof(T)));
+  CUDA_TRY(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+template <class T>
+int create_tables(tcfd_ns2d* h, const tcfd_ns2d_desc_t* d) {
+  const int n = h->n, nh = h->nh;
+  // twiddles exp(-2 pi i j / n), evaluated in double
+  std::vector<T> tw(2 * (size_t)n);
+  const double PI = 3.14159265358979323846264338327950288;
+  for (int j = 0; j < n; ++j) {
+    // exact octant symmetries are not needed at this accuracy: cos/sin of double arguments
+    const double a = -2.0 * PI * (double)j / (double)n;
+    tw[2 * j] = (T)std::cos(a);
+    tw[2 * j + 1] = (T)std::sin(a);
+  }
+  int rc;
+  if ((rc = upload<T>(&h->tw, tw.data(), tw.size()))) return rc;
+  // kappa / n^2 : exact (n is a power of two) -- carries the 1/n^2 of the inverse transforms
+  const T scale = (T)(1.0 / ((double)n * (double)n));
+  std::vector<T> kx(n), ky(nh);
+  for (int i = 0; i < n; ++i) kx[i] = static_cast<const T*>(d->kappa_x)[i] * scale;
+  for (int i = 0; i < nh; ++i) ky[i] = static_cast<const T*>(d->kappa_y)[i] * scale;
+  if ((rc = upload<T>(&h->kappa_x, kx.data(), n))) return rc;
+  if ((rc = upload<T>(&h->kappa_y, ky.data(), nh))) return rc;
+  if ((rc = upload<T>(&h->nil, d->neg_inv_lap, (size_t)n * nh))) return rc;
+  if ((rc = upload<T>(&h->lin, d->linear_term, (size_t)n * nh))) return rc;
+  h->KF = nh;
+  if (d->filter) {
+    if ((rc = upload<T>(&h->filt, d->filter, (size_t)n * nh))) return rc;
+    // rows |kx| that carry at least one unmasked mode
+    const T* f = static_cast<const T*>(d->filter);
+    int kf = 0;
+    for (int p = 0; p < nh; ++p) {
+      const int r1 = p, r2 = (n - p) % n;
+      bool any = false;
+      for (int c = 0; c < nh && !any; ++c) any = (f[(size_t)r1 * nh + c] != T(0)) || (f[(size_t)r2 * nh + c] != T(0));
+      if (any) kf = p + 1;
+    }
+    h->KF = kf > 0 ? kf : 1;
+  }
+  return 0;
+}
+
+template <class T>
+void fill_params(const tcfd_ns2d* h, tcfd::NsParams<T>& p, int batch) {
+  std::memset(&p, 0, sizeof(p));
+  p.B = batch;
+  p.KF = h->KF;
+  p.H = static_cast<tcfd::cx<T>*>(h->H);
+  p.advt = static_cast<tcfd::cx<T>*>(h->advt);
+  p.tw = static_cast<const tcfd::cx<T>*>(h->tw);
+  p.kappa_x = static_cast<const T*>(h->kappa_x);
+  p.kappa_y = static_cast<const T*>(h->kappa_y);
+  p.nil = static_cast<const T*>(h->nil);
+  p.lin = static_cast<const T*>(h->lin);
+  p.filt = static_cast<const T*>(h->filt);
+  p.fhat = static_cast<const tcfd::cx<T>*>(h->fhat);
+}
+
+int launch(tcfd_ns2d* h, int which, const void* params, void* stream) {
+  int rc = h->entry.launch(which, params, h->num_sms, stream);
+  h->launches++;
+  if (rc != 0) return fail(TCFD_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+  return 0;
+}
+
+template <class T>
+int step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int batch, int steps, int nstages,
+              const double* beta, const double* gdt, const double* mu, double inv_total_dt, void* stream) {
+  typedef tcfd::cx<T> C;
+  tcfd::NsParams<T> p;
+  fill_params<T>(h, p, batch);
+  const int total = steps * nstages;
+  // prologue: H[4] from the initial state
+  p.w_in = static_cast<const C*>(w_in);
+  int rc;
+  if ((rc = launch(h, TCFD_K_ROWS_INV, &p, stream))) return rc;
+  const C* src = static_cast<const C*>(w_in);
+  for (int j = 0; j < total; ++j) {
+    const int k = j % nstages;
+    if ((rc = launch(h, TCFD_K_COLS, &p, stream))) return rc;
+    C* dst = ((total - 1 - j) % 2 == 0) ? static_cast<C*>(w_out) : static_cast<C*>(h->wS);
+    p.mode = tcfd::UPD_RK;
+    p.w_in = src;
+    p.w_out = dst;
+    p.h_in = static_cast<const C*>((j % 2) ? h->hB : h->hA);
+    p.h_out = static_cast<C*>((j % 2) ? h->hA : h->hB);
+    p.read_h = (k > 0 && beta[k] != 0.0) ? 1 : 0;
+    p.write_h = (k + 1 < nstages && beta[k + 1] != 0.0) ? 1 : 0;
+    p.beta = (T)beta[k];
+    p.gdt = (T)gdt[k];
+    p.mu = (T)mu[k];
+    const bool last = (j == total - 1);
+    p.w_old = nullptr;
+    p.dwdt = nullptr;
+    if (last && dwdt) {
+      p.w_old = static_cast<const C*>(w_in);
+      p.dwdt = static_cast<C*>(dwdt);
+      p.inv_tdt = (T)inv_total_dt;
+    }
+    if ((rc = launch(h, last ? TCFD_K_ROWS_FWD : TCFD_K_ROWS_FULL, &p, stream))) return rc;
+    src = dst;
+  }
+  return 0;
+}
+
+template <class T>
+int eval_impl(tcfd_ns2d* h, int mode, const void* w_in, const void* wt_in, void* out, int batch, void* stream) {
+  typedef tcfd::cx<T> C;
+  tcfd::NsParams<T> p;
+  fill_params<T>(h, p, batch);
+  p.w_in = static_cast<const C*>(w_in);
+  int rc;
+  if ((rc = launch(h, TCFD_K_ROWS_INV, &p, stream))) return rc;
+  if ((rc = launch(h, TCFD_K_COLS, &p, stream))) return rc;
+  p.mode = mode;
+  p.w_old = static_cast<const C*>(wt_in);
+  p.h_out = static_cast<C*>(out);
+  return launch(h, TCFD_K_ROWS_FWD, &p, stream);
+}
+
+int check_batch(const tcfd_ns2d* h, int batch) {
+  if (!h) return fail(TCFD_ERR_INVALID, "null handle");
+  if (batch < 1 || batch > h->max_batch)
+    return fail(TCFD_ERR_INVALID, "batch " + std::to_string(batch) + " outside [1, max_batch=" + std::to_string(h->max_batch) + "]");
+  return 0;
+}
+}  // namespace
+
+extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
+  if (!out || !d) return fail(TCFD_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (d->prec != 32 && d->prec != 64) return fail(TCFD_ERR_INVALID, "prec must be 32 or 64");
+  if (d->max_batch < 1) return fail(TCFD_ERR_INVALID, "max_batch must be >= 1");
+  if (!d->kappa_x || !d->kappa_y || !d->neg_inv_lap || !d->linear_term)
+    return fail(TCFD_ERR_INVALID, "kappa_x, kappa_y, neg_inv_lap and linear_term are required");
+  tcfd_ns2d_entry_t e{};
+  if (!find_entry(d->prec, d->n, &e))
+    return fail(TCFD_ERR_INVALID, "unsupported grid size n=" + std::to_string(d->n) +
+                                      " (supported: powers of two 32..2048)");
+  tcfd_ns2d* h = new tcfd_ns2d();
+  h->n = d->n;
+  h->nh = d->n / 2 + 1;
+  h->prec = d->prec;
+  h->es = d->prec / 8;
+  h->max_batch = d->max_batch;
+  h->entry = e;
+#ifndef TCFD_EMU
+  {
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (ce != cudaSuccess) {
+      delete h;
+      return fail(TCFD_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(ce));
+    }
+  }
+#endif
+  int rc = (d->prec == 32) ? create_tables<float>(h, d) : create_tables<double>(h, d);
+  if (rc == 0 && d->f_hat) rc = tcfd_ns2d_set_forcing(h, d->f_hat);
+  if (rc == 0) {
+    const size_t sb = h->state_bytes(h->max_batch);
+    void** bufs[] = {&h->hA, &h->hB, &h->wS, &h->advt};
+    for (void** b : bufs) {
+      if (cudaMalloc(b, sb) != cudaSuccess) { rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed"); break; }
+      h->ws_bytes += sb;
+    }
+    // H: [B][nh][n/yt][4][yt] = 4 * nh * n complex per sample
+    const size_t hb = (size_t)h->max_batch * h->nh * h->n * 4 * 2 * h->es;
+    if (rc == 0) {
+      if (cudaMalloc(&h->H, hb) != cudaSuccess) rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed");
+      else h->ws_bytes += hb;
+    }
+  }
+  if (rc != 0) {
+    std::string keep = g_err;
+    tcfd_ns2d_destroy(h);
+    g_err = keep;
+    return rc;
+  }
+  *out = h;
+  return TCFD_OK;
+}
+
+extern "C" int tcfd_ns2d_destroy(tcfd_ns2d_t* h) {
+  if (!h) return TCFD_OK;
+  void* all[] = {h->tw, h->kappa_x, h->kappa_y, h->nil, h->lin, h->filt, h->fhat, h->hA, h->hB,
+                 h->wS, h->H, h->advt, h->stage_in, h->stage_out, h->stage_dw};
+  for (void* p : all)
+    if (p) cudaFree(p);
+  delete h;
+  return TCFD_OK;
+}
+
+extern "C" int tcfd_ns2d_set_forcing(tcfd_ns2d_t* h, const void* f_hat) {
+  if (!h) return fail(TCFD_ERR_INVALID, "null handle");
+  const size_t bytes = (size_t)h->n * h->nh * 2 * h->es;
+  if (!f_hat) {
+    if (h->fhat) cudaFree(h->fhat);
+    h->fhat = nullptr;
+    return TCFD_OK;
+  }
+  if (!h->fhat) CUDA_TRY(cudaMalloc(&h->fhat, bytes));
+  CUDA_TRY(cudaMemcpy(h->fhat, f_hat, bytes, cudaMemcpyHostToDevice));
+  return TCFD_OK;
+}
+
+extern "C" size_t tcfd_ns2d_workspace_bytes(const tcfd_ns2d_t* h) { return h ? h->ws_bytes : 0; }
+extern "C" int tcfd_ns2d_last_launch_count(const tcfd_ns2d_t* h) { return h ? h->launches : 0; }
+
+extern "C" int tcfd_ns2d_step(tcfd_ns2d_t* h, const void* w_in, void* w_out, void* dwdt, int batch, int steps,
+                              int nstages, const double* beta, const double* gdt, const double* mu,
+                              double inv_total_dt, void* stream) {
+  int rc = check_batch(h, batch);
+  if (rc) return rc;
+  if (!w_in || !w_out || !beta || !gdt || !mu) return fail(TCFD_ERR_INVALID, "null argument");
+  if (w_in == w_out) return fail(TCFD_ERR_INVALID, "w_out must not alias w_in");
+  if (steps < 1 || nstages < 1) return fail(TCFD_ERR_INVALID, "steps and nstages must be >= 1");
+  h->launches = 0;
+  return h->prec == 32
+             ? step_impl<float>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream)
+             : step_impl<double>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream);
+}
+
+extern "C" int tcfd_ns2d_explicit_terms(tcfd_ns2d_t* h, const void* w_in, void* f_out, int batch, void* stream) {
+  int rc = check_batch(h, batch);
+  if (rc) return rc;
+  if (!w_in || !f_out) return fail(TCFD_ERR_INVALID, "null argument");
+  h->launches = 0;
+  return h->prec == 32 ? eval_impl<float>(h, tcfd::UPD_F, w_in, nullptr, f_out, batch, stream)
+                       : eval_impl<double>(h, tcfd::UPD_F, w_in, nullptr, f_out, batch, stream);
+}
+
+extern "C" int tcfd_ns2d_residual(tcfd_ns2d_t* h, const void* w_in, const void* wt_in, void* r_out, int batch,
+                                  void* stream) {
+  int rc = check_batch(h, batch);
+  if (rc) return rc;
+  if (!w_in || !wt_in || !r_out) return fail(TCFD_ERR_INVALID, "null argument");
+  h->launches = 0;
+  return h->prec == 32 ? eval_impl<float>(h, tcfd::UPD_RESID, w_in, wt_in, r_out, batch, stream)
+                       : eval_impl<double>(h, tcfd::UPD_RESID, w_in, wt_in, r_out, batch, stream);
+}
+
+extern "C" int tcfd_ns2d_step_host(tcfd_ns2d_t* h, const void* w_in_host, void* w_out_host, void* dwdt_host,
+                                   int batch, int steps, int nstages, const double* beta, const double* gdt,
+                                   const double* mu, double inv_total_dt, void* stream_) {
+  int rc = check_batch(h, batch);
+  if (rc) return rc;
+  if (!w_in_host || !w_out_host) return fail(TCFD_ERR_INVALID, "null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t sb = h->state_bytes(h->max_batch);
+  if (!h->stage_in) { CUDA_TRY(cudaMalloc(&h->stage_in, sb)); h->ws_bytes += sb; }
+  if (!h->stage_out) { CUDA_TRY(cudaMalloc(&h->stage_out, sb)); h->ws_bytes += sb; }
+  if (dwdt_host && !h->stage_dw) { CUDA_TRY(cudaMalloc(&h->stage_dw, sb)); h->ws_bytes += sb; }
+  const size_t nb = h->state_bytes(batch);
+  CUDA_TRY(cudaMemcpyAsync(h->stage_in, w_in_host, nb, cudaMemcpyHostToDevice, stream));
+  rc = tcfd_ns2d_step(h, h->stage_in, h->stage_out, dwdt_host ? h->stage_dw : nullptr, batch, steps, nstages,
+                      beta, gdt, mu, inv_total_dt, stream_);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(w_out_host, h->stage_out, nb, cudaMemcpyDeviceToHost, stream));
+  if (dwdt_host) CUDA_TRY(cudaMemcpyAsync(dwdt_host, h->stage_dw, nb, cudaMemcpyDeviceToHost, stream));
+  return TCFD_OK;
+}

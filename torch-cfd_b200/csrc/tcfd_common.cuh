@@ -1,0 +1,26 @@
+// Common definitions for the torch-cfd B200 kernels.
+#pragma once
+#ifdef TCFD_EMU
+#include "tcfd_emu.h"
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#define TCFD_HD __host__ __device__ __forceinline__
+#define TCFD_D __device__ __forceinline__
+#define TCFD_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define TCFD_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
+namespace tcfd {
+
+template <class T>
+struct alignas(2 * sizeof(T)) cx {
+  T x, y;
+};
+template <class T> TCFD_HD cx<T> operator+(cx<T> a, cx<T> b) { return cx<T>{a.x + b.x, a.y + b.y}; }
+template <class T> TCFD_HD cx<T> operator-(cx<T> a, cx<T> b) { return cx<T>{a.x - b.x, a.y - b.y}; }
+template <class T> TCFD_HD cx<T> operator*(T s, cx<T> a) { return cx<T>{s * a.x, s * a.y}; }
+template <class T> TCFD_HD cx<T> conj(cx<T> a) { return cx<T>{a.x, -a.y}; }
+
+}  // namespace tcfd

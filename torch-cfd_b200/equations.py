@@ -1,0 +1,291 @@
+"""Drop-in ``NavierStokes2DSpectral`` / ``RK4CrankNicolsonStepper`` backed by the fused sm_100a
+kernels of libtcfd (reference: torch_cfd/equations.py:35-107, :249-463).
+
+Same constructor arguments, buffer names (``kx, ky, laplace, linear_term, filter``), methods
+(``forward/step, explicit_terms, implicit_terms, implicit_solve, residual``) and return values as
+the reference.  Differences, all deliberate:
+
+* the equation runs on CUDA tensors only -- there is no CPU fallback; a CPU tensor raises;
+* ``forward`` with an ``RK4CrankNicolsonStepper`` is ONE call into the C ABI for all ``steps``
+  (2 kernel launches per RK substage, no torch.fft, no eager elementwise kernels);
+* the forcing must be state independent (both shipped spectral forcings are): its spectrum is
+  evaluated once and added inside the kernel instead of 5x per step;
+* the solver is inference-only (``torch.no_grad`` semantics), like every shipped caller.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .grids import Grid
+from .spectral import brick_wall_filter_2d, spectral_laplacian_2d
+
+Params = Dict[str, torch.Tensor]
+
+
+def stable_time_step(dx: float = None, dt: float = None, viscosity: float = None,
+                     max_velocity: float = 2.0, max_courant_number: float = 0.5,
+                     implicit_diffusion: bool = True, ndim: int = 2) -> float:
+    """Host scalar helper (reference: torch_cfd/equations.py:35-64): the advection CFL bound,
+    tightened by the diffusive bound when diffusion is explicit, never larger than ``dt``."""
+    dt_adv = max_courant_number * dx / max_velocity
+    if not implicit_diffusion:
+        dt_adv = min(dt_adv, dx**2 / (viscosity * 2**ndim))
+    return min(dx, dt_adv, dt) if dt is not None else min(dx, dt_adv)
+
+
+class ImplicitExplicitODE(nn.Module):
+    """du/dt = F(u) + G(u) with F explicit and G implicit (reference: equations.py:67-107)."""
+
+    def explicit_terms(self, u):
+        raise NotImplementedError
+
+    def implicit_terms(self, u):
+        raise NotImplementedError
+
+    def implicit_solve(self, u, step_size):
+        raise NotImplementedError
+
+    def residual(self, u, u_t):
+        raise NotImplementedError
+
+
+_CK = {
+    "alphas": [0, 0.1496590219993, 0.3704009573644, 0.6222557631345, 0.9582821306748, 1],
+    "betas": [0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257],
+    "gammas": [0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681],
+}
+_RK4 = {
+    "alphas": [0.0, 0.5, 0.5, 1.0, 1.0],
+    # upstream writes integer zeros here, which makes its constructor raise (nn.Parameter of an
+    # int64 tensor, torch_cfd/equations.py:322,167); floats make the documented option usable
+    "betas": [0.0, 0.0, 0.0, 0.0],
+    "gammas": [1 / 6, 1 / 3, 1 / 3, 1 / 6],
+}
+
+
+class RK4CrankNicolsonStepper(nn.Module):
+    """Low-storage Runge-Kutta (Carpenter-Kennedy 2N) for the explicit terms with Crank-Nicolson
+    for the implicit ones (reference: torch_cfd/equations.py:249-358).
+
+    ``params`` holds ``alphas`` (len s+1), ``betas`` and ``gammas`` (len s) exactly like upstream.
+    For a libtcfd-backed equation the whole step is fused on the GPU; any other
+    ``ImplicitExplicitODE`` takes the generic sub-stage loop.
+    """
+
+    def __init__(self, order: float = 4, requires_grad: bool = False, weights: Optional[Params] = None,
+                 low_storage: bool = True, *args, **kwargs):
+        super().__init__()
+        self.order = order
+        table = _CK if low_storage else _RK4
+        params = {k: torch.tensor(v) for k, v in table.items()}
+        self.params = nn.ParameterDict({k: nn.Parameter(v, requires_grad=requires_grad) for k, v in params.items()})
+        self.requires_grad = requires_grad
+
+    def substage_scalars(self, dt: float, params: Optional[Params] = None):
+        """(beta_k, gamma_k*dt, mu_k) for every substage, evaluated with the same tensor
+        arithmetic (and therefore the same rounding) as upstream equations.py:355-357."""
+        params = self.params if params is None else params
+        alphas, betas, gammas = params["alphas"], params["betas"], params["gammas"]
+        beta, gdt, mu = [], [], []
+        for k in range(len(betas)):
+            beta.append(float(betas[k]))
+            gdt.append(float(gammas[k] * dt))
+            mu.append(float(0.5 * dt * (alphas[k + 1] - alphas[k])))
+        return beta, gdt, mu
+
+    def forward(self, u: torch.Tensor, dt: float, equation: ImplicitExplicitODE,
+                params: Optional[Params] = None) -> torch.Tensor:
+        if isinstance(equation, NavierStokes2DSpectral):
+            return equation._fused_steps(u, dt, 1, self, params, want_dudt=False)[0]
+        params = self.params if params is None else params
+        alphas, betas, gammas = params["alphas"], params["betas"], params["gammas"]
+        F, G, G_inv = equation.explicit_terms, equation.implicit_terms, equation.implicit_solve
+        h = 0
+        for k in range(len(betas)):
+            h = F(u) + betas[k] * h
+            mu = 0.5 * dt * (alphas[k + 1] - alphas[k])
+            u = G_inv(u + gammas[k] * dt * h + mu * G(u), mu)
+        return u
+
+
+def _probe_state_independent(forcing_fn, grid: Grid, vorticity: bool) -> bool:
+    n = grid.shape[0]
+    g = torch.Generator().manual_seed(0)
+
+    def state():
+        if vorticity:
+            return torch.randn(n, n // 2 + 1, generator=g, dtype=torch.get_default_dtype()).to(torch.complex64)
+        return (torch.randn(n, n, generator=g), torch.randn(n, n, generator=g))
+
+    def flat(out):
+        outs = out if isinstance(out, (tuple, list)) else (out,)
+        return [getattr(o, "data", o) for o in outs]
+
+    a, b = flat(forcing_fn(grid, state())), flat(forcing_fn(grid, state()))
+    return all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+class NavierStokes2DSpectral(ImplicitExplicitODE):
+    """2-D vorticity Navier-Stokes, pseudo-spectral, explicit advection + implicit diffusion
+    (reference: torch_cfd/equations.py:361-463).
+
+    Args:
+      viscosity, grid, drag, smooth (2/3 rule), forcing_fn, solver: as upstream.
+    """
+
+    def __init__(self, viscosity: float, grid: Grid, drag: float = 0.0, smooth: bool = True,
+                 forcing_fn: Optional[Callable] = None, solver: Optional[nn.Module] = None, **kwargs):
+        super().__init__()
+        self.viscosity = viscosity
+        self.grid = grid
+        self.drag = drag
+        self.smooth = smooth
+        self.forcing_fn = forcing_fn
+        self.solver = solver
+        self._plans = {}
+        self._initialize()
+
+    def _initialize(self):
+        kx, ky = self.grid.rfft_mesh()
+        self.register_buffer("kx", kx)
+        self.register_buffer("ky", ky)
+        laplace = -4 * (torch.pi) ** 2 * (abs(self.kx) ** 2 + abs(self.ky) ** 2)
+        self.register_buffer("laplace", laplace)
+        filter_ = brick_wall_filter_2d(self.grid)
+        linear_term = self.viscosity * self.laplace - self.drag
+        self.register_buffer("linear_term", linear_term)
+        self.register_buffer("filter", filter_)
+
+    # ------------------------------------------------------------------ plan management
+    def forcing_hat(self) -> Optional[torch.Tensor]:
+        """Spectrum of the (state-independent) forcing exactly as upstream adds it in every
+        substage (equations.py:429-437), evaluated once on the host."""
+        if self.forcing_fn is None:
+            return None
+        fn = self.forcing_fn
+        vorticity = bool(getattr(fn, "vorticity", False))
+        known = getattr(fn, "state_independent", False) or type(fn).__name__ == "KolmogorovForcing"
+        if not known and not _probe_state_independent(fn, self.grid, vorticity):
+            raise NotImplementedError(
+                "torch-cfd_b200: forcing_fn depends on the state; only state-independent forcings "
+                "(e.g. KolmogorovForcing) can be fused into the CUDA step")
+        kx, ky = self.kx.cpu(), self.ky.cpu()
+        if vorticity:
+            f = fn(self.grid, None)
+            return torch.fft.rfft2(getattr(f, "data", f).cpu())
+        fx, fy = fn(self.grid, None)
+        fx_hat = torch.fft.rfft2(getattr(fx, "data", fx).cpu())
+        fy_hat = torch.fft.rfft2(getattr(fy, "data", fy).cpu())
+        return 2j * torch.pi * (fy_hat * kx - fx_hat * ky)
+
+    def invalidate_plan(self):
+        """Drop cached device plans (call after editing a buffer or the forcing)."""
+        for p in self._plans.values():
+            p.close()
+        self._plans = {}
+
+    def _plan(self, device: torch.device, batch: int) -> "_lib.NS2DPlan":
+        if device.type != "cuda":
+            raise RuntimeError(
+                "torch-cfd_b200 runs the spectral step on CUDA devices only (no CPU fallback); "
+                f"got a tensor on {device}. Move the state to a B200 first.")
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        plan = self._plans.get(key)
+        if plan is not None and plan.max_batch >= batch:
+            return plan
+        if plan is not None:
+            plan.close()
+        lib = _lib.load_library()
+        kx, ky = self.kx.detach().cpu(), self.ky.detach().cpu()
+        dtype = kx.dtype
+        n = kx.shape[0]
+        kappa_x = (2j * torch.pi * kx).imag[:, 0]
+        kappa_y = (2j * torch.pi * ky).imag[0, :]
+        neg_inv_lap = -1 / spectral_laplacian_2d((kx, ky))
+        filt = self.filter.detach().cpu() if self.smooth else None
+        with torch.cuda.device(key):
+            plan = _lib.NS2DPlan(lib, n, dtype, batch, kappa_x, kappa_y, neg_inv_lap,
+                                 self.linear_term.detach().cpu(), filt, self.forcing_hat())
+        self._plans[key] = plan
+        return plan
+
+    def _as_batch(self, t: torch.Tensor) -> Tuple[torch.Tensor, torch.Size]:
+        n, nh = self.kx.shape
+        if t.dim() < 2 or tuple(t.shape[-2:]) != (n, nh):
+            raise ValueError(f"expected a spectrum of shape (*, {n}, {nh}), got {tuple(t.shape)}")
+        want = torch.complex64 if self.kx.dtype == torch.float32 else torch.complex128
+        if t.dtype != want:
+            raise TypeError(f"expected {want} (equation buffers are {self.kx.dtype}), got {t.dtype}")
+        return t.detach().reshape(-1, n, nh).contiguous(), t.shape
+
+    # ------------------------------------------------------------------ reference API
+    @torch.no_grad()
+    def explicit_terms(self, vort_hat):
+        w, shape = self._as_batch(vort_hat)
+        out = torch.empty_like(w)
+        with torch.cuda.device(w.device):
+            self._plan(w.device, w.shape[0]).explicit_terms(w, out)
+        return out.reshape(shape)
+
+    def implicit_terms(self, vort_hat):
+        return self.linear_term * vort_hat
+
+    def implicit_solve(self, vort_hat, dt):
+        return 1 / (1 - dt * self.linear_term) * vort_hat
+
+    @torch.no_grad()
+    def residual(self, vhat: torch.Tensor, vt_hat: torch.Tensor):
+        w, shape = self._as_batch(vhat)
+        wt, _ = self._as_batch(vt_hat)
+        out = torch.empty_like(w)
+        with torch.cuda.device(w.device):
+            self._plan(w.device, w.shape[0]).residual(w, wt, out)
+        return out.reshape(shape)
+
+    def step(self, *args, **kwargs):
+        return self.forward(*args, **kwargs)
+
+    @torch.no_grad()
+    def _fused_steps(self, vort_hat, dt, steps, solver, params=None, want_dudt=True):
+        w, shape = self._as_batch(vort_hat)
+        beta, gdt, mu = solver.substage_scalars(dt, params)
+        out = torch.empty_like(w)
+        dwdt = torch.empty_like(w) if want_dudt else None
+        with torch.cuda.device(w.device):
+            self._plan(w.device, w.shape[0]).step(w, out, dwdt, steps, beta, gdt, mu, 1 / (steps * dt))
+        return out.reshape(shape), (dwdt.reshape(shape) if want_dudt else None)
+
+    def forward(self, vort_hat, dt, steps=1) -> Tuple[torch.Tensor, torch.Tensor]:
+        """vort_hat: (B, n, n//2+1), (n_t, n, n//2+1) or (n, n//2+1) complex spectrum.
+        Returns (vort_hat after ``steps`` steps, (new - old) / (steps * dt))."""
+        if isinstance(self.solver, RK4CrankNicolsonStepper):
+            return self._fused_steps(vort_hat, dt, steps, self.solver)
+        if self.solver is None:
+            raise TypeError("NavierStokes2DSpectral.solver is None: pass solver=RK4CrankNicolsonStepper()")
+        vort_old = vort_hat
+        for _ in range(steps):
+            vort_hat = self.solver(vort_hat, dt, self)
+        return vort_hat, 1 / (steps * dt) * (vort_hat - vort_old)
+
+    @torch.no_grad()
+    def forward_host(self, vort_hat_host: torch.Tensor, dt, steps=1, device=None):
+        """End-to-end variant for HOST-resident states: uploads the (preferably pinned) CPU
+        tensor, steps on the GPU and downloads both results (tcfd_ns2d_step_host).  Returns pinned
+        CPU tensors; synchronises the stream before returning."""
+        if vort_hat_host.is_cuda:
+            raise ValueError("forward_host expects a CPU tensor")
+        if not isinstance(self.solver, RK4CrankNicolsonStepper):
+            raise TypeError("forward_host needs an RK4CrankNicolsonStepper")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        w, shape = self._as_batch(vort_hat_host)
+        beta, gdt, mu = self.solver.substage_scalars(dt)
+        out = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
+        dwdt = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
+        with torch.cuda.device(dev):
+            self._plan(dev, w.shape[0]).step(w, out, dwdt, steps, beta, gdt, mu, 1 / (steps * dt), host=True)
+            torch.cuda.current_stream().synchronize()
+        return out.reshape(shape), dwdt.reshape(shape)
