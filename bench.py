@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Benchmark of hot path A: RK4+CN pseudo-spectral vorticity steps per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--n 512] [--batch 64] [--dtype fp32|fp64]
+
+Workload (BASELINE.json north_star target, SURVEY.md 8d row "T"): Kolmogorov-forced 2-D vorticity,
+512 x 512 grid, batch 64 PER GPU, fp32, nu = 1e-3, drag 0.1, dt = 1e-3, 2/3 de-aliasing,
+Carpenter-Kennedy RK4 + Crank-Nicolson.  One "step" = one full RK4 step (5 substages) of the
+whole batch.  Weak scaling: every rank steps its own 64 samples, no data-path collective.
+
+Prints ONE JSON line (rank 0).  `value` = steps/s with the state resident in HBM (CUDA events,
+max over ranks); `e2e` = the same through the host-buffer API call (pinned H2D of the state,
+step, D2H of both results inside the timed region); `roofline` = algorithmic bytes of the step
+(18 * S * B, S = one half spectrum) over its device time against the measured HBM copy
+bandwidth; `cpu_baseline` = the oracle port of the reference's CPU path on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+VISC, DRAG, DT = 1e-3, 0.1, 1e-3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_state(n, batch, dtype, first_index):
+    """Seeded synthetic periodic-box vorticity spectra (CPU generator => device independent).
+    4 seeded fields per rank, rescaled per sample so all samples differ (cheap for large batches)."""
+    from oracle import ns2d_oracle as O
+    base = O.synthetic_vorticity_hat(n, 4, 1000, dtype, first_index=0)
+    w = torch.empty(batch, n, n // 2 + 1, dtype=base.dtype)
+    for i in range(batch):
+        w[i] = base[(first_index + i) % 4] * (1.0 + 0.002 * ((first_index + i) % 97))
+    return w
+
+
+def cpu_reference_steps_per_s(n, batch, dtype, steps, threads):
+    """The reference's CPU path (oracle port: same torch ops in the same order, pinned bit-exactly
+    to the reference by tests/test_oracle_cpu.py) on the host cores; 1 warm-up + `steps` timed."""
+    from oracle import ns2d_oracle as O
+    torch.set_num_threads(threads)
+    diam = 2 * torch.pi
+    tb = O.make_tables(n, diam, VISC, DRAG, True, ("vorticity", O.kolmogorov_forcing_vorticity(n, diam, dtype)), dtype)
+    w = make_state(n, batch, dtype, 0)
+    with torch.no_grad():
+        w, _ = O.forward(tb, w, DT, 1)
+        t0 = time.perf_counter()
+        w, _ = O.forward(tb, w, DT, steps)
+        el = time.perf_counter() - t0
+    return steps / el, el
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dtype = torch.float32 if a.dtype == "fp32" else torch.float64
+    threads = os.cpu_count() or 1
+    k = max(1, a.steps)
+    # bounded: the run must end within minutes -> cap the timed steps by a ~60 s budget
+    per, el1 = cpu_reference_steps_per_s(a.n, a.batch, dtype, 1, threads)
+    k = max(1, min(k, int(60.0 * per)))
+    v, el = cpu_reference_steps_per_s(a.n, a.batch, dtype, k, threads)
+    sample = f"{k} full steps of the {a.batch} x {a.n}^2 batch after 1 warm-up step, torch CPU, {threads} threads"
+    unit = f"steps/s (one step = {a.batch} x {a.n}^2 samples, RK4+CN)"
+    print(json.dumps({
+        "impl": "reference", "metric": "rk4_spectral_steps_per_sec", "value": v, "unit": unit,
+        "n_gpus": a.gpus, "steps": k, "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "f64",
+        "data": "synthetic",
+        "config": {"workload": f"Kolmogorov-forced 2D vorticity RK4+CN, {a.n}x{a.n}, batch {a.batch}, {a.dtype}",
+                   "note": "CPU arm: rank 0 only, one batch regardless of --gpus"},
+        "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    import torch_cfd_b200 as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float32 if a.dtype == "fp32" else torch.float64
+    torch.set_default_dtype(dtype)
+    n, B, K, W = a.n, a.batch, a.steps, max(3, a.warmup)
+    diam = 2 * torch.pi
+    grid = T.Grid(shape=(n, n), domain=((0, diam), (0, diam)))
+    forcing = T.KolmogorovForcing(diam=diam, wave_number=1, grid=grid, scale=1, vorticity=True)
+    ns = T.NavierStokes2DSpectral(viscosity=VISC, grid=grid, drag=DRAG, smooth=True, forcing_fn=forcing,
+                                  solver=T.RK4CrankNicolsonStepper())
+    w_host = make_state(n, B, dtype, rank * B).pin_memory()
+    w = w_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return x
+
+    # ---------------- device-resident: K steps, one step per API call
+    for _ in range(W):
+        w, _ = ns(w, DT, steps=1)
+    plan = ns._plans[local]
+    sampler = ClockSampler(local)
+    launches = 0
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        w, _ = ns(w, DT, steps=1)
+        launches += plan.last_launch_count
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    assert torch.isfinite(torch.view_as_real(w)).all().item(), "state blew up"
+    value = world * K / (ms * 1e-3)
+
+    # ---------------- per-kernel device times (separate instrumented pass, same workload)
+    kt = plan.kernel_times(w, DT, ns.solver, steps=3)
+
+    # ---------------- end to end: host (pinned) buffers through the public host API
+    e2e = None
+    if not a.no_e2e:
+        Ke = max(3, min(K, 20))
+        for _ in range(3):
+            out_h, dw_h = ns.forward_host(w_host, DT, steps=1)
+        barrier()
+        t0 = time.perf_counter()
+        cur = w_host
+        for _ in range(Ke):
+            cur, dw_h = ns.forward_host(cur, DT, steps=1)
+        barrier()
+        el = max_over_ranks(time.perf_counter() - t0)
+        sb = w_host.numel() * w_host.element_size()
+        e2e = {"value": world * Ke / el, "unit": None, "h2d_bytes_per_step": sb, "d2h_bytes_per_step": 2 * sb,
+               "steps": Ke}
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    es = 4 if dtype == torch.float32 else 8
+    S = n * (n // 2 + 1) * 2 * es
+    alg_bytes_step = 18 * S * B
+    peak, peak_src = peaks()
+    achieved = alg_bytes_step * K / (ms * 1e-3) / 1e9  # per GPU
+    unit = f"steps/s (one step = {B} x {n}^2 samples per GPU, RK4+CN)"
+    if e2e:
+        e2e["unit"] = unit
+    out = {
+        "metric": "rk4_spectral_steps_per_sec", "value": value, "unit": unit, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
+        "config": {"workload": f"Kolmogorov-forced 2D vorticity RK4+CN, {n}x{n}, batch {B} per GPU, {a.dtype}",
+                   "global_batch": B * world, "viscosity": VISC, "drag": DRAG, "dt": DT,
+                   "l2": f"working set (state w+h {2 * S * B / 1e6:.0f} MB + workspace) exceeds the 126 MB L2; no flush",
+                   "sample_steps_per_s": value * B, "cell_steps_per_s": value * B * n * n},
+        "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": alg_bytes_step,
+                     "note": "whole step (all launches); per-kernel device times in `kernels`"},
+        "kernels": kt,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        v, el = cpu_reference_steps_per_s(n, B, dtype, a.cpu_steps, threads)
+        out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                               "sample": f"{a.cpu_steps} full steps of the {B} x {n}^2 batch after 1 warm-up, "
+                                         f"oracle port of the reference (torch CPU), {el:.1f} s"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

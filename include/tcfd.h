@@ -82,6 +82,14 @@ int tcfd_ns2d_step(tcfd_ns2d_t* h, const void* w_in, void* w_out, void* dwdt, in
                    int nstages, const double* beta, const double* gdt, const double* mu,
                    double inv_total_dt, void* stream);
 
+/* Measurement twin of tcfd_ns2d_step (no reference counterpart): brackets EVERY kernel launch of
+ * the step with CUDA events on `stream`, synchronises the stream, and returns the summed device
+ * time ms[4] and launch count count[4] per kernel kind (0 = rows-inverse prologue, 1 = rows
+ * forward+inverse, 2 = rows forward epilogue, 3 = cols).  Used by bench.py for the roofline. */
+int tcfd_ns2d_step_timed(tcfd_ns2d_t* h, const void* w_in, void* w_out, int batch, int steps, int nstages,
+                         const double* beta, const double* gdt, const double* mu, void* stream, float* ms,
+                         int* count);
+
 /* NavierStokes2DSpectral.explicit_terms(vort_hat)  (torch_cfd/equations.py:413-441) */
 int tcfd_ns2d_explicit_terms(tcfd_ns2d_t* h, const void* w_in, void* f_out, int batch, void* stream);
 

@@ -1,0 +1,149 @@
+"""CPU tier for hot path A: the product kernels compiled for host threads (tests/emu/libtcfd_emu.so,
+-DTCFD_EMU, test infrastructure only) against the reference-generated goldens and the oracle;
+the C-ABI surface of the product library; host-side logic of the nn.Module shims."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from _common import (O, ROOT, default_dtype, emu_plan, load_golden, oracle_tables, rel_l2,
+                     substage_scalars)
+
+
+def _golden_tables(g, dtype):
+    return oracle_tables(int(g["n"]), dtype, float(g["viscosity"]), float(g["drag"]), str(g["forcing"]),
+                         True, float(g["diam"]))
+
+
+@pytest.mark.parametrize("name,dtype,tol", [
+    ("ns2d_c1_fp64", torch.float64, 1e-12),
+    ("ns2d_fp32_unforced", torch.float32, 2e-6),
+    ("ns2d_fp64_velforce", torch.float64, 1e-12),
+])
+def test_emu_kernels_vs_reference_golden(name, dtype, tol):
+    g = load_golden(name)
+    tb = _golden_tables(g, dtype)
+    w0 = torch.from_numpy(g["w0_hat"]).reshape(-1, tb.n, tb.n // 2 + 1)
+    plan = emu_plan(tb, w0.shape[0], dtype)
+    dt = float(g["dt"])
+    beta, gdt, mu = substage_scalars(dtype, dt)
+    F = torch.empty_like(w0)
+    plan.explicit_terms(w0, F)
+    assert rel_l2(F, torch.from_numpy(g["F0"]).reshape(F.shape)) < tol
+    for s in (1, 2):
+        if f"w_{s}" not in g.files:
+            continue
+        out, dw = torch.empty_like(w0), torch.empty_like(w0)
+        plan.step(w0, out, dw, s, beta, gdt, mu, 1 / (s * dt))
+        assert plan.last_launch_count == 1 + 2 * 5 * s
+        assert rel_l2(out, torch.from_numpy(g[f"w_{s}"]).reshape(out.shape)) < tol
+        # dw/dt is a difference of nearly equal states: looser in relative terms
+        assert rel_l2(dw, torch.from_numpy(g[f"dwdt_{s}"]).reshape(out.shape)) < tol * 1e4
+    r = torch.empty_like(w0)
+    w1 = torch.from_numpy(g["w_1"]).reshape(w0.shape)
+    d1 = torch.from_numpy(g["dwdt_1"]).reshape(w0.shape)
+    plan.residual(w1, d1, r)
+    # the residual is a cancellation (w_t - F - L w ~ 0): measure its error on the scale of w_t
+    rr = torch.from_numpy(g["res_1"]).reshape(w0.shape)
+    assert (torch.linalg.norm(r - rr) / torch.linalg.norm(d1)).item() < tol
+
+
+@pytest.mark.parametrize("n,batch,dtype,forcing,smooth", [
+    (32, 3, torch.float32, "vorticity", True),
+    (128, 2, torch.float64, None, True),
+    (64, 5, torch.float32, "velocity", False),
+    (256, 1, torch.float32, "vorticity", True),
+])
+def test_emu_kernels_vs_oracle(n, batch, dtype, forcing, smooth):
+    tb = oracle_tables(n, dtype, 1e-3, 0.1, forcing, smooth)
+    w0 = O.synthetic_vorticity_hat(n, batch, 7, dtype)
+    plan = emu_plan(tb, batch, dtype)
+    dt = 1e-3
+    beta, gdt, mu = substage_scalars(dtype, dt)
+    out = torch.empty_like(w0)
+    plan.step(w0, out, None, 2, beta, gdt, mu, 1 / (2 * dt))
+    ref, _ = O.forward(tb, w0, dt, 2)
+    assert rel_l2(out, ref) < (1e-12 if dtype == torch.float64 else 2e-6)
+
+
+def test_emu_batch_smaller_than_plan_and_errors():
+    tb = oracle_tables(32, torch.float32)
+    plan = emu_plan(tb, 4, torch.float32)
+    w0 = O.synthetic_vorticity_hat(32, 4, 1, torch.float32)
+    beta, gdt, mu = substage_scalars(torch.float32, 1e-3)
+    full = torch.empty_like(w0)
+    plan.step(w0, full, None, 1, beta, gdt, mu, 1e3)
+    part = torch.empty_like(w0[:3])
+    plan.step(w0[:3].contiguous(), part, None, 1, beta, gdt, mu, 1e3)
+    assert torch.equal(part, full[:3])  # samples are independent: bit-identical
+    with pytest.raises(RuntimeError, match="alias"):
+        plan.step(w0, w0, None, 1, beta, gdt, mu, 1e3)
+    with pytest.raises(ValueError):
+        plan.step(w0[:, :16].contiguous(), full, None, 1, beta, gdt, mu, 1e3)
+    big = torch.cat([w0, w0])
+    with pytest.raises(RuntimeError, match="max_batch"):
+        plan.step(big, torch.empty_like(big), None, 1, beta, gdt, mu, 1e3)
+
+
+def test_unsupported_size_is_reported():
+    from torch_cfd_b200 import _lib
+    from _common import ensure_emu_lib
+    lib = _lib.TcfdLibrary(ensure_emu_lib())
+    n = 48
+    z = torch.zeros(n, n // 2 + 1)
+    with pytest.raises(RuntimeError, match="unsupported grid size"):
+        _lib.NS2DPlan(lib, n, torch.float32, 1, torch.zeros(n), torch.zeros(n // 2 + 1), z, z, None, None)
+
+
+def test_product_library_exports_every_declared_symbol():
+    """libtcfd.so (nvcc, sm_100a) loads without a GPU and exports all of include/tcfd.h."""
+    hdr = open(os.path.join(ROOT, "include", "tcfd.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(tcfd_[a-z0-9_]+)\s*\(", hdr)))
+    assert "tcfd_ns2d_step" in names and "tcfd_last_error" in names
+    path = os.path.join(ROOT, "torch-cfd_b200", "libtcfd.so")
+    if not os.path.exists(path):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(path)
+    for nm in names:
+        assert hasattr(lib, nm), nm
+    lib.tcfd_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.tcfd_version()
+
+
+def test_module_host_logic_matches_reference_tables():
+    """Buffers, mask, forcing spectrum and substage scalars of the shim == reference goldens."""
+    import torch_cfd_b200 as T
+    from _common import build_module
+    for name, dtype in [("ns2d_c1_fp64", torch.float64), ("ns2d_fp32_n128_nobatch", torch.float32),
+                        ("ns2d_fp64_velforce", torch.float64)]:
+        g = load_golden(name)
+        with default_dtype(dtype):
+            ns = build_module(int(g["n"]), dtype, float(g["viscosity"]), float(g["drag"]), str(g["forcing"]))
+            for key in ["kx", "ky", "laplace", "linear_term", "filter"]:
+                assert np.array_equal(getattr(ns, key).numpy(), g[key]), (name, key)
+            tb = _golden_tables(g, dtype)
+            assert torch.equal(ns.forcing_hat(), O.forcing_hat(tb))
+            assert ns.solver.substage_scalars(float(g["dt"])) == substage_scalars(dtype, float(g["dt"]))
+            w0 = torch.from_numpy(g["w0_hat"])
+            assert np.array_equal(ns.implicit_terms(w0).numpy(), g["G0"])
+            assert np.array_equal(ns.implicit_solve(w0, 0.5 * float(g["dt"])).numpy(), g["solve0"])
+    gm = load_golden("mask_bounds")
+    for n in [16, 32, 64, 128, 256, 512, 1024, 2048]:
+        m = T.brick_wall_filter_2d(T.Grid((n, n), domain=((0, 1), (0, 1))))
+        from torch_cfd_b200.spectral import brick_wall_bounds
+        assert list(brick_wall_bounds(n)) + [int(m.sum())] == gm[f"n{n}"].tolist()
+
+
+def test_module_refuses_cpu_and_bad_inputs():
+    from _common import build_module
+    with default_dtype(torch.float32):
+        ns = build_module(64, torch.float32)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ns(torch.zeros(1, 64, 33, dtype=torch.complex64), 1e-3)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ns.explicit_terms(torch.zeros(64, 33, dtype=torch.complex64))

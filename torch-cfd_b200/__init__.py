@@ -1,2 +1,9 @@
 """torch-cfd_b200: B200-native (sm_100a) implementation of torch-cfd's spectral hot path."""
 __version__ = "0.1.0"
+
+from .grids import Grid  # noqa: F401
+from .forcings import ForcingFn, KolmogorovForcing  # noqa: F401
+from .spectral import (brick_wall_filter_2d, fft_mesh_2d, spectral_curl_2d, spectral_div_2d,  # noqa: F401
+                       spectral_grad_2d, spectral_laplacian_2d, spectral_rot_2d, vorticity_to_velocity)
+from .equations import (ImplicitExplicitODE, NavierStokes2DSpectral, RK4CrankNicolsonStepper,  # noqa: F401
+                        stable_time_step)

@@ -54,6 +54,8 @@ class TcfdLibrary:
         c.tcfd_ns2d_last_launch_count.argtypes = [vp]
         c.tcfd_ns2d_step.argtypes = [vp, vp, vp, vp, ci, ci, ci, dp, dp, dp, ctypes.c_double, vp]
         c.tcfd_ns2d_step_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, dp, dp, dp, ctypes.c_double, vp]
+        c.tcfd_ns2d_step_timed.argtypes = [vp, vp, vp, ci, ci, ci, dp, dp, dp, vp,
+                                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
         c.tcfd_ns2d_explicit_terms.argtypes = [vp, vp, vp, ci, vp]
         c.tcfd_ns2d_residual.argtypes = [vp, vp, vp, vp, ci, vp]
 
@@ -158,6 +160,26 @@ class NS2DPlan:
                 w_in.shape[0], int(steps), len(beta), _darr(beta), _darr(gdt), _darr(mu),
                 float(inv_total_dt), stream)
         self.lib.check(rc, "tcfd_ns2d_step")
+
+    KERNEL_KINDS = ("rows_inv", "rows_fwd_inv", "rows_fwd", "cols")
+
+    def kernel_times(self, w_in: torch.Tensor, dt: float, solver, steps: int = 1):
+        """Instrumented pass (tcfd_ns2d_step_timed): per-kernel-kind device time of `steps` steps.
+        Returns {kind: {"launches": c, "ms_total": t, "us_per_launch": ...}}."""
+        self._check_state(w_in, "w_in")
+        beta, gdt, mu = solver.substage_scalars(dt)
+        out = torch.empty_like(w_in)
+        ms = (ctypes.c_float * 4)()
+        cnt = (ctypes.c_int * 4)()
+        rc = self.lib.c.tcfd_ns2d_step_timed(self._h, w_in.data_ptr(), out.data_ptr(), w_in.shape[0], int(steps),
+                                             len(beta), _darr(beta), _darr(gdt), _darr(mu), _stream_handle(w_in),
+                                             ms, cnt)
+        self.lib.check(rc, "tcfd_ns2d_step_timed")
+        res = {"steps": steps}
+        for i, k in enumerate(self.KERNEL_KINDS):
+            res[k] = {"launches": cnt[i], "ms_total": ms[i],
+                      "us_per_launch": (1e3 * ms[i] / cnt[i]) if cnt[i] else None}
+        return res
 
     def explicit_terms(self, w_in: torch.Tensor, out: torch.Tensor):
         self._check_state(w_in, "w_in")

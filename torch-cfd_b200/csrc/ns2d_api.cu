@@ -50,6 +50,10 @@ struct tcfd_ns2d {
   void *stage_in = nullptr, *stage_out = nullptr, *stage_dw = nullptr;  // step_host staging
   size_t ws_bytes = 0;
   int launches = 0;
+  // measurement mode (tcfd_ns2d_step_timed): every launch is bracketed by events
+  bool timed = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_kind;
   size_t state_bytes(int b) const { return (size_t)b * n * nh * 2 * es; }
 };
 
@@ -127,7 +131,19 @@ void fill_params(const tcfd_ns2d* h, tcfd::NsParams<T>& p, int batch) {
 }
 
 int launch(tcfd_ns2d* h, int which, const void* params, void* stream) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timed) {
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, static_cast<cudaStream_t>(stream)));
+  }
   int rc = h->entry.launch(which, params, h->num_sms, stream);
+  if (h->timed) {
+    CUDA_TRY(cudaEventRecord(e1, static_cast<cudaStream_t>(stream)));
+    h->ev.push_back(e0);
+    h->ev.push_back(e1);
+    h->ev_kind.push_back(which);
+  }
   h->launches++;
   if (rc != 0) return fail(TCFD_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
   return 0;
@@ -289,6 +305,30 @@ extern "C" int tcfd_ns2d_step(tcfd_ns2d_t* h, const void* w_in, void* w_out, voi
   return h->prec == 32
              ? step_impl<float>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream)
              : step_impl<double>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream);
+}
+
+extern "C" int tcfd_ns2d_step_timed(tcfd_ns2d_t* h, const void* w_in, void* w_out, int batch, int steps, int nstages,
+                                    const double* beta, const double* gdt, const double* mu, void* stream,
+                                    float* ms, int* count) {
+  if (!h || !ms || !count) return fail(TCFD_ERR_INVALID, "null argument");
+  h->timed = true;
+  int rc = tcfd_ns2d_step(h, w_in, w_out, nullptr, batch, steps, nstages, beta, gdt, mu, 0.0, stream);
+  h->timed = false;
+  for (int i = 0; i < 4; ++i) { ms[i] = 0.f; count[i] = 0; }
+  cudaError_t ce = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  for (size_t i = 0; i < h->ev_kind.size(); ++i) {
+    float t = 0.f;
+    if (ce == cudaSuccess && rc == 0) ce = cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]);
+    ms[h->ev_kind[i]] += t;
+    count[h->ev_kind[i]]++;
+    cudaEventDestroy(h->ev[2 * i]);
+    cudaEventDestroy(h->ev[2 * i + 1]);
+  }
+  h->ev.clear();
+  h->ev_kind.clear();
+  if (rc) return rc;
+  if (ce != cudaSuccess) return fail(TCFD_ERR_CUDA, std::string("timed step: ") + cudaGetErrorString(ce));
+  return TCFD_OK;
 }
 
 extern "C" int tcfd_ns2d_explicit_terms(tcfd_ns2d_t* h, const void* w_in, void* f_out, int batch, void* stream) {

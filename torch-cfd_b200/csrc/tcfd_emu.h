@@ -90,3 +90,8 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std
 inline cudaError_t cudaGetLastError() { return 0; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+typedef void* cudaEvent_t;
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+inline cudaError_t cudaEventElapsedTime(float* t, cudaEvent_t, cudaEvent_t) { *t = 0.f; return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }

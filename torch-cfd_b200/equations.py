@@ -215,6 +215,10 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
 
     def _as_batch(self, t: torch.Tensor) -> Tuple[torch.Tensor, torch.Size]:
         n, nh = self.kx.shape
+        if t.device.type != "cuda":
+            raise RuntimeError(
+                "torch-cfd_b200 runs the spectral step on CUDA devices only (no CPU fallback); "
+                f"got a tensor on {t.device}. Move the state to a B200 first.")
         if t.dim() < 2 or tuple(t.shape[-2:]) != (n, nh):
             raise ValueError(f"expected a spectrum of shape (*, {n}, {nh}), got {tuple(t.shape)}")
         want = torch.complex64 if self.kx.dtype == torch.float32 else torch.complex128
