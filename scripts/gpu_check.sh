@@ -19,4 +19,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 # full capture of the two substage kernels (skip warm-up launches)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ns2d_ -s 12 -c 2 -o $OUT/prof_full -f \
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_full.log 2>&1
+if [ -x scripts/microbench/fp32_pipe ]; then timeout 120 scripts/microbench/fp32_pipe > $OUT/microbench_fp32_pipe.txt 2>&1; fi
+if [ -n "$SANITIZE" ]; then
+  timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/racecheck.log 2>&1
+  timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/memcheck.log 2>&1
+  tail -3 $OUT/racecheck.log $OUT/memcheck.log
+fi
 ls -la $OUT

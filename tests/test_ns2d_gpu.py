@@ -59,11 +59,12 @@ def test_c1_100_steps_meets_north_star_bar():
         e = rel_l2(torch.fft.irfft2(w.cpu()), torch.fft.irfft2(torch.from_numpy(g["w_100"])))
         assert e < 1e-6  # the bar
         assert e < 1e-11  # what we actually get
-        # stepping 100 x 1 is the same computation as 1 x 100
+        # stepping 100 x 1 is the same computation as 1 x 100 (the fused kernel re-derives the
+        # self-conjugate rows from registers instead of re-reading them: rounding-level difference)
         w1 = torch.from_numpy(g["w0_hat"]).to(DEV)
         for _ in range(100):
             w1, _ = ns(w1, float(g["dt"]), steps=1)
-        assert torch.equal(w1, w)
+        assert rel_l2(w1, w) < 1e-14
 
 
 @pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024])

@@ -66,8 +66,10 @@ TCFD_HD cx<T> mul_i_dir(cx<T> a) {  // a * (DIR * i)
 }
 template <int DIR, class T>
 TCFD_HD cx<T> tw_mul(cx<T> a, cx<T> w) {  // a * w (forward) or a * conj(w) (inverse); w has forward sign
-  if (DIR < 0) return cx<T>{a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x};
-  return cx<T>{a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y};
+  // the library is compiled with -fmad=false: these are the only fused multiply-adds of the FFT,
+  // so every kernel instantiation rounds identically
+  if (DIR < 0) return cx<T>{fma_rn(a.x, w.x, -(a.y * w.y)), fma_rn(a.x, w.y, a.y * w.x)};
+  return cx<T>{fma_rn(a.x, w.x, a.y * w.y), fma_rn(a.y, w.x, -(a.x * w.y))};
 }
 
 template <int DIR, class T>

@@ -2,6 +2,7 @@
 // launch sequence of one RK4+CN step; the arithmetic lives in ns2d_kernels.cuh.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,7 @@ bool find_entry(int prec, int n, tcfd_ns2d_entry_t* e) {
 
 struct tcfd_ns2d {
   int n = 0, nh = 0, prec = 0, max_batch = 0, KF = 0, num_sms = 1;
+  int chunk = 1;  // samples per L2-resident chunk
   size_t es = 0;  // sizeof(real)
   tcfd_ns2d_entry_t entry{};
   void *tw = nullptr, *kappa_x = nullptr, *kappa_y = nullptr, *nil = nullptr, *lin = nullptr,
@@ -150,41 +152,51 @@ int launch(tcfd_ns2d* h, int which, const void* params, void* stream) {
 }
 
 template <class T>
-int step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int batch, int steps, int nstages,
+int step_impl(tcfd_ns2d* h, const void* w_in_, void* w_out_, void* dwdt_, int batch, int steps, int nstages,
               const double* beta, const double* gdt, const double* mu, double inv_total_dt, void* stream) {
   typedef tcfd::cx<T> C;
-  tcfd::NsParams<T> p;
-  fill_params<T>(h, p, batch);
   const int total = steps * nstages;
-  // prologue: H[4] from the initial state
-  p.w_in = static_cast<const C*>(w_in);
-  int rc;
-  if ((rc = launch(h, TCFD_K_ROWS_INV, &p, stream))) return rc;
-  const C* src = static_cast<const C*>(w_in);
-  for (int j = 0; j < total; ++j) {
-    const int k = j % nstages;
-    if ((rc = launch(h, TCFD_K_COLS, &p, stream))) return rc;
-    C* dst = ((total - 1 - j) % 2 == 0) ? static_cast<C*>(w_out) : static_cast<C*>(h->wS);
-    p.mode = tcfd::UPD_RK;
-    p.w_in = src;
-    p.w_out = dst;
-    p.h_in = static_cast<const C*>((j % 2) ? h->hB : h->hA);
-    p.h_out = static_cast<C*>((j % 2) ? h->hA : h->hB);
-    p.read_h = (k > 0 && beta[k] != 0.0) ? 1 : 0;
-    p.write_h = (k + 1 < nstages && beta[k + 1] != 0.0) ? 1 : 0;
-    p.beta = (T)beta[k];
-    p.gdt = (T)gdt[k];
-    p.mu = (T)mu[k];
-    const bool last = (j == total - 1);
-    p.w_old = nullptr;
-    p.dwdt = nullptr;
-    if (last && dwdt) {
-      p.w_old = static_cast<const C*>(w_in);
-      p.dwdt = static_cast<C*>(dwdt);
-      p.inv_tdt = (T)inv_total_dt;
+  const size_t per = (size_t)h->n * h->nh;  // spectrum entries per sample
+  // Chunk-major schedule: all substages of all steps run on `chunk` samples before the next chunk
+  // starts, so a chunk's state (w, h), H and advt stay resident in the 126 MB L2 from launch to
+  // launch and HBM sees each state entry once per call instead of 18 S per step.
+  for (int c0 = 0; c0 < batch; c0 += h->chunk) {
+    const int cb = (batch - c0 < h->chunk) ? batch - c0 : h->chunk;
+    const C* w_in = static_cast<const C*>(w_in_) + (size_t)c0 * per;
+    C* w_out = static_cast<C*>(w_out_) + (size_t)c0 * per;
+    C* dwdt = dwdt_ ? static_cast<C*>(dwdt_) + (size_t)c0 * per : nullptr;
+    tcfd::NsParams<T> p;
+    fill_params<T>(h, p, cb);
+    // prologue: H[4] from the initial state
+    p.w_in = w_in;
+    int rc;
+    if ((rc = launch(h, TCFD_K_ROWS_INV, &p, stream))) return rc;
+    const C* src = w_in;
+    for (int j = 0; j < total; ++j) {
+      const int k = j % nstages;
+      if ((rc = launch(h, TCFD_K_COLS, &p, stream))) return rc;
+      C* dst = ((total - 1 - j) % 2 == 0) ? w_out : static_cast<C*>(h->wS);
+      p.mode = tcfd::UPD_RK;
+      p.w_in = src;
+      p.w_out = dst;
+      p.h_in = static_cast<const C*>((j % 2) ? h->hB : h->hA);
+      p.h_out = static_cast<C*>((j % 2) ? h->hA : h->hB);
+      p.read_h = (k > 0 && beta[k] != 0.0) ? 1 : 0;
+      p.write_h = (k + 1 < nstages && beta[k + 1] != 0.0) ? 1 : 0;
+      p.beta = (T)beta[k];
+      p.gdt = (T)gdt[k];
+      p.mu = (T)mu[k];
+      const bool last = (j == total - 1);
+      p.w_old = nullptr;
+      p.dwdt = nullptr;
+      if (last && dwdt) {
+        p.w_old = w_in;
+        p.dwdt = dwdt;
+        p.inv_tdt = (T)inv_total_dt;
+      }
+      if ((rc = launch(h, last ? TCFD_K_ROWS_FWD : TCFD_K_ROWS_FULL, &p, stream))) return rc;
+      src = dst;
     }
-    if ((rc = launch(h, last ? TCFD_K_ROWS_FWD : TCFD_K_ROWS_FULL, &p, stream))) return rc;
-    src = dst;
   }
   return 0;
 }
@@ -192,16 +204,21 @@ int step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int batch
 template <class T>
 int eval_impl(tcfd_ns2d* h, int mode, const void* w_in, const void* wt_in, void* out, int batch, void* stream) {
   typedef tcfd::cx<T> C;
-  tcfd::NsParams<T> p;
-  fill_params<T>(h, p, batch);
-  p.w_in = static_cast<const C*>(w_in);
-  int rc;
-  if ((rc = launch(h, TCFD_K_ROWS_INV, &p, stream))) return rc;
-  if ((rc = launch(h, TCFD_K_COLS, &p, stream))) return rc;
-  p.mode = mode;
-  p.w_old = static_cast<const C*>(wt_in);
-  p.h_out = static_cast<C*>(out);
-  return launch(h, TCFD_K_ROWS_FWD, &p, stream);
+  const size_t per = (size_t)h->n * h->nh;
+  for (int c0 = 0; c0 < batch; c0 += h->chunk) {
+    const int cb = (batch - c0 < h->chunk) ? batch - c0 : h->chunk;
+    tcfd::NsParams<T> p;
+    fill_params<T>(h, p, cb);
+    p.w_in = static_cast<const C*>(w_in) + (size_t)c0 * per;
+    int rc;
+    if ((rc = launch(h, TCFD_K_ROWS_INV, &p, stream))) return rc;
+    if ((rc = launch(h, TCFD_K_COLS, &p, stream))) return rc;
+    p.mode = mode;
+    p.w_old = wt_in ? static_cast<const C*>(wt_in) + (size_t)c0 * per : nullptr;
+    p.h_out = static_cast<C*>(out) + (size_t)c0 * per;
+    if ((rc = launch(h, TCFD_K_ROWS_FWD, &p, stream))) return rc;
+  }
+  return 0;
 }
 
 int check_batch(const tcfd_ns2d* h, int batch) {
@@ -244,14 +261,23 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
   int rc = (d->prec == 32) ? create_tables<float>(h, d) : create_tables<double>(h, d);
   if (rc == 0 && d->f_hat) rc = tcfd_ns2d_set_forcing(h, d->f_hat);
   if (rc == 0) {
-    const size_t sb = h->state_bytes(h->max_batch);
+    // chunk: the per-chunk working set (H = 4 spectra-sized complex fields per sample dominates)
+    // is kept under TCFD_CHUNK_MB (default 40 MB) so that it stays L2-resident between launches
+    double budget_mb = 40.0;
+    if (const char* e = getenv("TCFD_CHUNK_MB")) budget_mb = atof(e) > 0 ? atof(e) : budget_mb;
+    const double per_sample_mb = (double)h->nh * h->n * 2 * h->es * 8.0 / 1e6;  // H(4) + advt + w, h, wS
+    int chunk = (int)(budget_mb / per_sample_mb);
+    if (chunk < 1) chunk = 1;
+    if (chunk > h->max_batch) chunk = h->max_batch;
+    h->chunk = chunk;
+    const size_t sb = h->state_bytes(h->chunk);
     void** bufs[] = {&h->hA, &h->hB, &h->wS, &h->advt};
     for (void** b : bufs) {
       if (cudaMalloc(b, sb) != cudaSuccess) { rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed"); break; }
       h->ws_bytes += sb;
     }
     // H: [B][nh][n/yt][4][yt] = 4 * nh * n complex per sample
-    const size_t hb = (size_t)h->max_batch * h->nh * h->n * 4 * 2 * h->es;
+    const size_t hb = (size_t)h->chunk * h->nh * h->n * 4 * 2 * h->es;
     if (rc == 0) {
       if (cudaMalloc(&h->H, hb) != cudaSuccess) rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed");
       else h->ws_bytes += hb;

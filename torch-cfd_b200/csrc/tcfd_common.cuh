@@ -23,4 +23,8 @@ template <class T> TCFD_HD cx<T> operator-(cx<T> a, cx<T> b) { return cx<T>{a.x 
 template <class T> TCFD_HD cx<T> operator*(T s, cx<T> a) { return cx<T>{s * a.x, s * a.y}; }
 template <class T> TCFD_HD cx<T> conj(cx<T> a) { return cx<T>{a.x, -a.y}; }
 
+// explicit fused multiply-add (the build disables implicit contraction, -fmad=false)
+TCFD_HD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
+TCFD_HD double fma_rn(double a, double b, double c) { return fma(a, b, c); }
+
 }  // namespace tcfd

@@ -213,9 +213,9 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         self._plans[key] = plan
         return plan
 
-    def _as_batch(self, t: torch.Tensor) -> Tuple[torch.Tensor, torch.Size]:
+    def _as_batch(self, t: torch.Tensor, host: bool = False) -> Tuple[torch.Tensor, torch.Size]:
         n, nh = self.kx.shape
-        if t.device.type != "cuda":
+        if t.device.type != "cuda" and not host:
             raise RuntimeError(
                 "torch-cfd_b200 runs the spectral step on CUDA devices only (no CPU fallback); "
                 f"got a tensor on {t.device}. Move the state to a B200 first.")
@@ -276,20 +276,28 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         return vort_hat, 1 / (steps * dt) * (vort_hat - vort_old)
 
     @torch.no_grad()
-    def forward_host(self, vort_hat_host: torch.Tensor, dt, steps=1, device=None):
+    def forward_host(self, vort_hat_host: torch.Tensor, dt, steps=1, device=None, out=None, dvdt_out=None):
         """End-to-end variant for HOST-resident states: uploads the (preferably pinned) CPU
         tensor, steps on the GPU and downloads both results (tcfd_ns2d_step_host).  Returns pinned
-        CPU tensors; synchronises the stream before returning."""
+        CPU tensors (``out`` / ``dvdt_out`` when given -- pass pre-allocated pinned buffers to
+        avoid a cudaHostAlloc per call); synchronises the stream before returning."""
         if vort_hat_host.is_cuda:
             raise ValueError("forward_host expects a CPU tensor")
         if not isinstance(self.solver, RK4CrankNicolsonStepper):
             raise TypeError("forward_host needs an RK4CrankNicolsonStepper")
+        if not torch.cuda.is_available():
+            raise RuntimeError("torch-cfd_b200: no CUDA device (there is no CPU fallback)")
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        w, shape = self._as_batch(vort_hat_host)
+        w, shape = self._as_batch(vort_hat_host, host=True)
         beta, gdt, mu = self.solver.substage_scalars(dt)
-        out = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
-        dwdt = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
+        if out is None:
+            out = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
+        if dvdt_out is None:
+            dvdt_out = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
+        o, d = out.view(w.shape), dvdt_out.view(w.shape)
+        if o.data_ptr() == w.data_ptr():
+            raise ValueError("out must not alias the input")
         with torch.cuda.device(dev):
-            self._plan(dev, w.shape[0]).step(w, out, dwdt, steps, beta, gdt, mu, 1 / (steps * dt), host=True)
+            self._plan(dev, w.shape[0]).step(w, o, d, steps, beta, gdt, mu, 1 / (steps * dt), host=True)
             torch.cuda.current_stream().synchronize()
-        return out.reshape(shape), dwdt.reshape(shape)
+        return o.view(shape), d.view(shape)
