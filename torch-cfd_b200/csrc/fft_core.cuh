@@ -12,6 +12,7 @@
 // memory only for the exchanges.
 #pragma once
 #include "tcfd_common.cuh"
+#include "packed.cuh"
 
 namespace tcfd {
 
@@ -61,11 +62,11 @@ TCFD_HD int fft_swz(int i) {
 // ---------------------------------------------------------------- butterflies
 // DIR = -1: forward (exp(-i...)), DIR = +1: inverse (exp(+i...)), un-normalised.
 template <int DIR, class T>
-TCFD_HD cx<T> mul_i_dir(cx<T> a) {  // a * (DIR * i)
+TCFD_D cx<T> mul_i_dir(cx<T> a) {  // a * (DIR * i)
   return DIR < 0 ? cx<T>{a.y, -a.x} : cx<T>{-a.y, a.x};
 }
-template <int DIR, class T>
-TCFD_HD cx<T> tw_mul(cx<T> a, cx<T> w) {  // a * w (forward) or a * conj(w) (inverse); w has forward sign
+template <int DIR, class T, class S>
+TCFD_D cx<T> tw_mul(cx<T> a, cx<S> w) {  // a * w (forward) or a * conj(w) (inverse); w has forward sign
   // the library is compiled with -fmad=false: these are the only fused multiply-adds of the FFT,
   // so every kernel instantiation rounds identically
   if (DIR < 0) return cx<T>{fma_rn(a.x, w.x, -(a.y * w.y)), fma_rn(a.x, w.y, a.y * w.x)};
@@ -73,14 +74,14 @@ TCFD_HD cx<T> tw_mul(cx<T> a, cx<T> w) {  // a * w (forward) or a * conj(w) (inv
 }
 
 template <int DIR, class T>
-TCFD_HD void radix2(cx<T>& a, cx<T>& b) {
+TCFD_D void radix2(cx<T>& a, cx<T>& b) {
   cx<T> t = a - b;
   a = a + b;
   b = t;
 }
 
 template <int DIR, class T>
-TCFD_HD void radix4(cx<T>& x0, cx<T>& x1, cx<T>& x2, cx<T>& x3) {
+TCFD_D void radix4(cx<T>& x0, cx<T>& x1, cx<T>& x2, cx<T>& x3) {
   cx<T> t0 = x0 + x2, t1 = x0 - x2, t2 = x1 + x3, t3 = mul_i_dir<DIR>(x1 - x3);
   x0 = t0 + t2;
   x2 = t0 - t2;
@@ -89,8 +90,8 @@ TCFD_HD void radix4(cx<T>& x0, cx<T>& x1, cx<T>& x2, cx<T>& x3) {
 }
 
 template <int DIR, class T>
-TCFD_HD void radix8(cx<T> (&v)[8]) {
-  const T h = T(0.70710678118654752440);
+TCFD_D void radix8(cx<T> (&v)[8]) {
+  const typename lane_traits<T>::scalar h = (typename lane_traits<T>::scalar)0.70710678118654752440;
   cx<T> b0 = v[0] + v[4], c0 = v[0] - v[4];
   cx<T> b1 = v[1] + v[5], c1 = v[1] - v[5];
   cx<T> b2 = v[2] + v[6], c2 = v[2] - v[6];
@@ -112,7 +113,7 @@ TCFD_HD void radix8(cx<T> (&v)[8]) {
 
 // ---------------------------------------------------------------- twiddle registers
 template <class T, int N>
-struct FftTwiddles {
+struct FftTwiddles {  // T: the SCALAR type (float twiddles serve both float and f2 data)
   static constexpr int NTW = fft_num_tw(N) > 0 ? fft_num_tw(N) : 1;
   cx<T> w[NTW];
 
@@ -149,8 +150,8 @@ struct FftTwiddles {
 // of a kernel must use the same HALF.  A write to half P at exchange e only needs every thread to
 // have finished reading half P at exchange e-2, which it did before the sync of exchange e-1).
 template <class T, int N, int DIR, int V, bool PP, int HALF, int P, class Sync>
-TCFD_D void fft_pass(cx<T> (&v)[V][8], const FftTwiddles<T, N>& tw, cx<T>* buf, int& parity, int t,
-                     Sync& sync) {
+TCFD_D void fft_pass(cx<T> (&v)[V][8], const FftTwiddles<typename lane_traits<T>::scalar, N>& tw, cx<T>* buf,
+                     int& parity, int t, Sync& sync) {
   constexpr int NT = N / 8;
   constexpr int NP = fft_num_passes(N);
   constexpr int r = fft_pass_radix(N, P), ns = fft_pass_ns(N, P), off = fft_tw_offset(N, P);
@@ -197,8 +198,8 @@ TCFD_D void fft_pass(cx<T> (&v)[V][8], const FftTwiddles<T, N>& tw, cx<T>* buf, 
 }
 
 template <class T, int N, int DIR, int V, bool PP, int HALF, class Sync>
-TCFD_D void fft_run(cx<T> (&v)[V][8], const FftTwiddles<T, N>& tw, cx<T>* buf, int& parity, int t,
-                    Sync& sync) {
+TCFD_D void fft_run(cx<T> (&v)[V][8], const FftTwiddles<typename lane_traits<T>::scalar, N>& tw, cx<T>* buf,
+                    int& parity, int t, Sync& sync) {
   static_assert(HALF >= V * N, "ping-pong half too small");
   fft_pass<T, N, DIR, V, PP, HALF, 0>(v, tw, buf, parity, t, sync);
 }

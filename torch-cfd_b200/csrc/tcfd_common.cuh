@@ -18,10 +18,10 @@ template <class T>
 struct alignas(2 * sizeof(T)) cx {
   T x, y;
 };
-template <class T> TCFD_HD cx<T> operator+(cx<T> a, cx<T> b) { return cx<T>{a.x + b.x, a.y + b.y}; }
-template <class T> TCFD_HD cx<T> operator-(cx<T> a, cx<T> b) { return cx<T>{a.x - b.x, a.y - b.y}; }
-template <class T> TCFD_HD cx<T> operator*(T s, cx<T> a) { return cx<T>{s * a.x, s * a.y}; }
-template <class T> TCFD_HD cx<T> conj(cx<T> a) { return cx<T>{a.x, -a.y}; }
+template <class T> TCFD_D cx<T> operator+(cx<T> a, cx<T> b) { return cx<T>{a.x + b.x, a.y + b.y}; }
+template <class T> TCFD_D cx<T> operator-(cx<T> a, cx<T> b) { return cx<T>{a.x - b.x, a.y - b.y}; }
+template <class T> TCFD_D cx<T> operator*(T s, cx<T> a) { return cx<T>{s * a.x, s * a.y}; }
+template <class T> TCFD_D cx<T> conj(cx<T> a) { return cx<T>{a.x, -a.y}; }
 
 // explicit fused multiply-add (the build disables implicit contraction, -fmad=false)
 TCFD_HD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
