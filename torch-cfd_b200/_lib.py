@@ -13,7 +13,8 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libtcfd.so")
+# TCFD_LIB: development override (an alternative build of the same CUDA library, e.g. a tuning variant)
+_LIB_PATH = os.environ.get("TCFD_LIB") or os.path.join(_HERE, "libtcfd.so")
 
 
 class _Desc(ctypes.Structure):

@@ -10,6 +10,10 @@
 #include "../../include/tcfd.h"
 #include "ns2d_kernels.cuh"
 #include "ns2d_plan.h"
+#include "tma.cuh"
+#ifndef TCFD_EMU
+#include <cudaTypedefs.h>
+#endif
 
 #define TCFD_DECL(prec, n) extern "C" void tcfd_ns2d_entry_##prec##_##n(tcfd_ns2d_entry_t*);
 #define TCFD_SIZES(X, prec) X(prec, 32) X(prec, 64) X(prec, 128) X(prec, 256) X(prec, 512) X(prec, 1024) X(prec, 2048)
@@ -47,9 +51,10 @@ struct tcfd_ns2d {
   size_t es = 0;  // sizeof(real)
   tcfd_ns2d_entry_t entry{};
   void *tw = nullptr, *kappa_x = nullptr, *kappa_y = nullptr, *nil = nullptr, *lin = nullptr,
-       *filt = nullptr, *fhat = nullptr;
-  void *hA = nullptr, *hB = nullptr, *wS = nullptr, *H = nullptr, *advt = nullptr;
+       *filt = nullptr, *fhat = nullptr, *tab = nullptr, *frow = nullptr, *tabU = nullptr, *maskU = nullptr;
+  void *hA = nullptr, *hB = nullptr, *wS = nullptr, *wT = nullptr, *H = nullptr, *advt = nullptr;
   void *stage_in = nullptr, *stage_out = nullptr, *stage_dw = nullptr;  // step_host staging
+  tcfd::TileMaps maps{};  // TMA descriptors of the H tiles (second-generation cols kernel)
   size_t ws_bytes = 0;
   int launches = 0;
   // measurement mode (tcfd_ns2d_step_timed): every launch is bracketed by events
@@ -113,6 +118,47 @@ int create_tables(tcfd_ns2d* h, const tcfd_ns2d_desc_t* d) {
     }
     h->KF = kf > 0 ? kf : 1;
   }
+  // interleaved copy {linear_term, mask, -1/laplace', 0} for the second-generation kernels
+  {
+    std::vector<tcfd::tab4<T>> tab((size_t)n * nh);
+    const T* lin = static_cast<const T*>(d->linear_term);
+    const T* nil = static_cast<const T*>(d->neg_inv_lap);
+    const T* f = static_cast<const T*>(d->filter);
+    for (size_t i = 0; i < tab.size(); ++i) tab[i] = tcfd::tab4<T>{lin[i], f ? f[i] : T(1), nil[i], T(0)};
+    if ((rc = upload<tcfd::tab4<T>>(&h->tab, tab.data(), tab.size()))) return rc;
+    std::vector<unsigned char> zero(n, 0);
+    if ((rc = upload<unsigned char>(&h->frow, zero.data(), n))) return rc;
+    if (h->entry.v2) {
+      // per-d blocks for the substage kernel: {lin_a, lin_b, nil_a, nil_b} per column (one copy serves
+      // rows r and n-r: the tables must be even in kx) and the 0/1 mask as bits per half
+      const int nd = n / 4 + 1;
+      const size_t tab_row = ((size_t)nh * 4 * sizeof(T) + 15) / 16 * 16, mask_row = ((size_t)nh + 15) / 16 * 16;
+      std::vector<unsigned char> tabU((size_t)nd * tab_row, 0), maskU((size_t)nd * 2 * mask_row, 0);
+      for (int r = 1; r < n; ++r)
+        for (int c = 0; c < nh; ++c)
+          if (lin[(size_t)r * nh + c] != lin[(size_t)(n - r) * nh + c] || nil[(size_t)r * nh + c] != nil[(size_t)(n - r) * nh + c])
+            return fail(TCFD_ERR_INVALID, "linear_term and neg_inv_lap must be even in kx (row r == row n-r)");
+      for (size_t i = 0; f && i < (size_t)n * nh; ++i)
+        if (f[i] != T(0) && f[i] != T(1)) return fail(TCFD_ERR_INVALID, "filter must be a 0/1 mask");
+      for (int dd = 0; dd < nd; ++dd) {
+        const int ra = 2 * dd, rb = (2 * dd + 1 <= n / 2) ? 2 * dd + 1 : ra;
+        const int rows[2][2] = {{ra, rb}, {(n - ra) % n, (n - rb) % n}};
+        T* tb = reinterpret_cast<T*>(tabU.data() + (size_t)dd * tab_row);
+        for (int c = 0; c < nh; ++c) {
+          tb[2 * c + 0] = lin[(size_t)ra * nh + c];  // plane 0: lin, lanes interleaved
+          tb[2 * c + 1] = lin[(size_t)rb * nh + c];
+          tb[2 * nh + c] = nil[(size_t)ra * nh + c];  // plane 1: nil of lane a
+          tb[3 * nh + c] = nil[(size_t)rb * nh + c];  // plane 2: nil of lane b
+          for (int hf = 0; hf < 2; ++hf) {
+            const bool ka = !f || f[(size_t)rows[hf][0] * nh + c] != T(0), kb = !f || f[(size_t)rows[hf][1] * nh + c] != T(0);
+            maskU[((size_t)dd * 2 + hf) * mask_row + c] = (unsigned char)((ka ? 1 : 0) | (kb ? 2 : 0));
+          }
+        }
+      }
+      if ((rc = upload<unsigned char>(&h->tabU, tabU.data(), tabU.size()))) return rc;
+      if ((rc = upload<unsigned char>(&h->maskU, maskU.data(), maskU.size()))) return rc;
+    }
+  }
   return 0;
 }
 
@@ -123,6 +169,15 @@ void fill_params(const tcfd_ns2d* h, tcfd::NsParams<T>& p, int batch) {
   p.KF = h->KF;
   p.H = static_cast<tcfd::cx<T>*>(h->H);
   p.advt = static_cast<tcfd::cx<T>*>(h->advt);
+  p.H2 = static_cast<T*>(h->H);
+  p.advt2 = static_cast<T*>(h->advt);
+  p.NDF = (h->KF + 1) / 2;
+  p.Hplane = (size_t)h->chunk * h->nh * h->n;
+  p.tab = static_cast<const tcfd::tab4<T>*>(h->tab);
+  p.frow = static_cast<const unsigned char*>(h->frow);
+  p.tabU = h->tabU;
+  if (const char* e = getenv("TCFD_DBG")) p.dbg = atoi(e);
+  p.maskU = static_cast<const unsigned char*>(h->maskU);
   p.tw = static_cast<const tcfd::cx<T>*>(h->tw);
   p.kappa_x = static_cast<const T*>(h->kappa_x);
   p.kappa_y = static_cast<const T*>(h->kappa_y);
@@ -132,6 +187,41 @@ void fill_params(const tcfd_ns2d* h, tcfd::NsParams<T>& p, int batch) {
   p.fhat = static_cast<const tcfd::cx<T>*>(h->fhat);
 }
 
+// TMA descriptors over H2 = [2 planes][chunk][NH][N] packed-complex entries (4 reals each): a tile
+// is 4 consecutive entries of every row of one sample, in both planes.
+int make_tile_maps(tcfd_ns2d* h) {
+  const size_t ent = 4 * h->es;
+  const size_t row_bytes = (size_t)h->n * ent;
+#ifdef TCFD_EMU
+  h->maps.base = static_cast<const unsigned char*>(h->H);
+  h->maps.row_bytes = row_bytes;
+  h->maps.sample_bytes = row_bytes * h->nh;
+  h->maps.plane_bytes = row_bytes * h->nh * h->chunk;
+  return 0;
+#else
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(TCFD_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+  auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  const CUtensorMapDataType dt = h->prec == 32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+  const CUtensorMapSwizzle sw = h->prec == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const cuuint64_t gdim[4] = {(cuuint64_t)h->n * 4, (cuuint64_t)h->nh, (cuuint64_t)h->chunk, 2};
+  const cuuint64_t gstr[3] = {(cuuint64_t)row_bytes, (cuuint64_t)row_bytes * h->nh, (cuuint64_t)row_bytes * h->nh * h->chunk};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint32_t rows = (cuuint32_t)((h->nh - 1) < 256 ? (h->nh - 1) : 256);
+  const cuuint32_t box_main[4] = {16, rows, 1, 2};  // 16 reals = 4 entries = 64 B (fp32) / 128 B (fp64)
+  const cuuint32_t box_last[4] = {16, 1, 1, 2};
+  CUresult r = encode(&h->maps.main, dt, 4, h->H, gdim, gstr, box_main, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS)
+    r = encode(&h->maps.last, dt, 4, h->H, gdim, gstr, box_last, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TCFD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return 0;
+#endif
+}
+
 int launch(tcfd_ns2d* h, int which, const void* params, void* stream) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timed) {
@@ -139,7 +229,7 @@ int launch(tcfd_ns2d* h, int which, const void* params, void* stream) {
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, static_cast<cudaStream_t>(stream)));
   }
-  int rc = h->entry.launch(which, params, h->num_sms, stream);
+  int rc = h->entry.launch(which, params, h->entry.v2 ? &h->maps : nullptr, h->num_sms, stream);
   if (h->timed) {
     CUDA_TRY(cudaEventRecord(e1, static_cast<cudaStream_t>(stream)));
     h->ev.push_back(e0);
@@ -175,12 +265,26 @@ int step_impl(tcfd_ns2d* h, const void* w_in_, void* w_out_, void* dwdt_, int ba
     for (int j = 0; j < total; ++j) {
       const int k = j % nstages;
       if ((rc = launch(h, TCFD_K_COLS, &p, stream))) return rc;
+      const bool last_sub = (j == total - 1);
       C* dst = ((total - 1 - j) % 2 == 0) ? w_out : static_cast<C*>(h->wS);
       p.mode = tcfd::UPD_RK;
       p.w_in = src;
       p.w_out = dst;
       p.h_in = static_cast<const C*>((j % 2) ? h->hB : h->hA);
       p.h_out = static_cast<C*>((j % 2) ? h->hA : h->hB);
+      if (h->entry.v2) {
+        // the state travels in the unit layout between substages (wS / wT), only the first
+        // substage reads and the last one writes the caller's reference layout
+        typedef tcfd::cx<typename tcfd::pack2<T>::type> CU;
+        p.in_user = (j == 0) ? 1 : 0;
+        p.out_user = last_sub ? 1 : 0;
+        p.w_in = w_in;    // reference-layout input (used when in_user; also dwdt's w_old)
+        p.w_out = w_out;  // reference-layout output (used when out_user)
+        p.wU_in = static_cast<const CU*>((j % 2) ? h->wS : h->wT);
+        p.wU_out = static_cast<CU*>((j % 2) ? h->wT : h->wS);
+        p.hU_in = static_cast<const CU*>((j % 2) ? h->hB : h->hA);
+        p.hU_out = static_cast<CU*>((j % 2) ? h->hA : h->hB);
+      }
       p.read_h = (k > 0 && beta[k] != 0.0) ? 1 : 0;
       p.write_h = (k + 1 < nstages && beta[k + 1] != 0.0) ? 1 : 0;
       p.beta = (T)beta[k];
@@ -216,7 +320,7 @@ int eval_impl(tcfd_ns2d* h, int mode, const void* w_in, const void* wt_in, void*
     p.mode = mode;
     p.w_old = wt_in ? static_cast<const C*>(wt_in) + (size_t)c0 * per : nullptr;
     p.h_out = static_cast<C*>(out) + (size_t)c0 * per;
-    if ((rc = launch(h, TCFD_K_ROWS_FWD, &p, stream))) return rc;
+    if ((rc = launch(h, TCFD_K_ROWS_EVAL, &p, stream))) return rc;
   }
   return 0;
 }
@@ -271,10 +375,17 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
     if (chunk > h->max_batch) chunk = h->max_batch;
     h->chunk = chunk;
     const size_t sb = h->state_bytes(h->chunk);
-    void** bufs[] = {&h->hA, &h->hB, &h->wS, &h->advt};
+    // advt: v1 [B][nh][n] complex; v2 [B][n/4+1][n][4 reals] (slightly larger)
+    const size_t ab = (size_t)h->chunk * (h->n / 4 + 1) * h->n * 4 * h->es;
+    // unit-layout state (v2): [B][n/4+1][2][nh] entries of 4 reals
+    const size_t ub = (size_t)h->chunk * (h->n / 4 + 1) * 2 * h->nh * 4 * h->es;
+    void** bufs[] = {&h->hA, &h->hB, &h->wS, &h->wT, &h->advt};
     for (void** b : bufs) {
-      if (cudaMalloc(b, sb) != cudaSuccess) { rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed"); break; }
-      h->ws_bytes += sb;
+      size_t nb = (b == &h->advt && ab > sb) ? ab : sb;
+      if (h->entry.v2 && b != &h->advt) nb = ub;
+      if (!h->entry.v2 && b == &h->wT) continue;
+      if (cudaMalloc(b, nb) != cudaSuccess) { rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed"); break; }
+      h->ws_bytes += nb;
     }
     // H: [B][nh][n/yt][4][yt] = 4 * nh * n complex per sample
     const size_t hb = (size_t)h->chunk * h->nh * h->n * 4 * 2 * h->es;
@@ -282,6 +393,7 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
       if (cudaMalloc(&h->H, hb) != cudaSuccess) rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed");
       else h->ws_bytes += hb;
     }
+    if (rc == 0 && h->entry.v2) rc = make_tile_maps(h);
   }
   if (rc != 0) {
     std::string keep = g_err;
@@ -295,7 +407,7 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
 
 extern "C" int tcfd_ns2d_destroy(tcfd_ns2d_t* h) {
   if (!h) return TCFD_OK;
-  void* all[] = {h->tw, h->kappa_x, h->kappa_y, h->nil, h->lin, h->filt, h->fhat, h->hA, h->hB,
+  void* all[] = {h->tw, h->kappa_x, h->kappa_y, h->nil, h->lin, h->filt, h->fhat, h->tab, h->frow, h->tabU, h->maskU, h->wT, h->hA, h->hB,
                  h->wS, h->H, h->advt, h->stage_in, h->stage_out, h->stage_dw};
   for (void* p : all)
     if (p) cudaFree(p);
@@ -313,6 +425,22 @@ extern "C" int tcfd_ns2d_set_forcing(tcfd_ns2d_t* h, const void* f_hat) {
   }
   if (!h->fhat) CUDA_TRY(cudaMalloc(&h->fhat, bytes));
   CUDA_TRY(cudaMemcpy(h->fhat, f_hat, bytes, cudaMemcpyHostToDevice));
+  // rows that carry a non-zero forcing entry (the kernels skip the f_hat loads of all other rows)
+  std::vector<unsigned char> frow(h->n, 0);
+  const size_t rb = (size_t)h->nh * 2 * h->es;
+  for (int r = 0; r < h->n; ++r) {
+    const unsigned char* row = static_cast<const unsigned char*>(f_hat) + (size_t)r * rb;
+    bool any = false;
+    if (h->prec == 32) {
+      const float* v = reinterpret_cast<const float*>(row);
+      for (int i = 0; i < 2 * h->nh && !any; ++i) any = v[i] != 0.0f;
+    } else {
+      const double* v = reinterpret_cast<const double*>(row);
+      for (int i = 0; i < 2 * h->nh && !any; ++i) any = v[i] != 0.0;
+    }
+    frow[r] = any ? 1 : 0;
+  }
+  CUDA_TRY(cudaMemcpy(h->frow, frow.data(), h->n, cudaMemcpyHostToDevice));
   return TCFD_OK;
 }
 

@@ -1,6 +1,7 @@
 // One translation unit per (precision, N): compiled with -DTCFD_PREC=32|64 -DTCFD_N=<n>.
-// Exports a C launcher table entry used by ns2d_api.cu.
-#include "ns2d_kernels.cuh"
+// Exports a C launcher table entry used by ns2d_api.cu.  N >= 256 gets the second-generation
+// kernels (ns2d_v2.cuh), smaller grids the CTA-tiled ones (ns2d_kernels.cuh).
+#include "ns2d_v2.cuh"
 #include "ns2d_plan.h"
 
 #if TCFD_PREC == 32
@@ -13,18 +14,8 @@ namespace {
 using namespace tcfd;
 constexpr int N = TCFD_N;
 constexpr int NT = N / 8;
-constexpr int CTA = 256;
-constexpr int G = (CTA / NT) > 0 ? (CTA / NT) : 1;
-constexpr int GC0 = G;
-constexpr int GC = GC0 < N / 2 ? GC0 : N / 2;
-constexpr int YT = 2 * GC;
-constexpr bool PP = true;
+constexpr bool V2 = N >= 256;
 typedef cx<real_t> cplx;
-
-constexpr size_t smem_rows(bool inv) { return (size_t)G * ((inv ? 2 : 1) * N) * (PP ? 2 : 1) * sizeof(cplx); }
-constexpr size_t smem_cols() {
-  return ((size_t)(N / 2 + 1) * (4 * YT + 1) + (size_t)GC * N * (PP ? 2 : 1)) * sizeof(cplx);
-}
 
 template <class K>
 int prep(K kernel, size_t smem, int threads, int* occ) {
@@ -33,56 +24,167 @@ int prep(K kernel, size_t smem, int threads, int* occ) {
   if (e != cudaSuccess) return (int)e;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kernel, threads, smem);
   if (e != cudaSuccess) return (int)e;
+  if (*occ < 1) *occ = 1;
 #else
   *occ = 1;
 #endif
   return 0;
 }
 
-int launch(int which, const void* params, int num_sms, void* stream_) {
-  const NsParams<real_t>& p = *static_cast<const NsParams<real_t>*>(params);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+inline int grid_for(int work, int num_sms, int o) {
+#ifdef TCFD_EMU
+  (void)num_sms;
+  (void)o;
+  return work;
+#else
+  const int cap = num_sms * (o > 0 ? o : 1);
+  return work < cap ? work : cap;
+#endif
+}
+
+#if TCFD_N < 256
+// ------------------------------------------------------------------ first generation (N <= 128)
+namespace v1 {
+constexpr int CTA = 256;
+constexpr int G = (CTA / NT) > 0 ? (CTA / NT) : 1;
+constexpr int GC = G < N / 2 ? G : N / 2;
+constexpr int YT = 2 * GC;
+constexpr bool PP = true;
+constexpr size_t smem_rows(bool inv) { return (size_t)G * ((inv ? 2 : 1) * N) * (PP ? 2 : 1) * sizeof(cplx); }
+constexpr size_t smem_cols() {
+  return ((size_t)(N / 2 + 1) * (4 * YT + 1) + (size_t)GC * N * (PP ? 2 : 1)) * sizeof(cplx);
+}
+
+int launch(int which, const NsParams<real_t>& p, int num_sms, cudaStream_t stream) {
   static int occ[4] = {0, 0, 0, 0};
   const int nblk_rows = (p.B * (N / 2 + 1) + G - 1) / G;
   const int ntiles = p.B * (N / YT);
   int rc = 0;
-  auto grid_for = [&](int work, int o) {
-#ifdef TCFD_EMU
-    (void)o;
-    return work;
-#else
-    int cap = num_sms * (o > 0 ? o : 1);
-    return work < cap ? work : cap;
-#endif
-  };
   switch (which) {
     case TCFD_K_ROWS_INV: {
       auto k = ns2d_rows_kernel<real_t, N, G, YT, false, true, PP>;
       if (!occ[0] && (rc = prep(k, smem_rows(true), G * NT, &occ[0]))) return rc;
-      TCFD_LAUNCH(k, grid_for(nblk_rows, occ[0]), G * NT, smem_rows(true), stream, p);
+      TCFD_LAUNCH(k, grid_for(nblk_rows, num_sms, occ[0]), G * NT, smem_rows(true), stream, p);
       break;
     }
     case TCFD_K_ROWS_FULL: {
       auto k = ns2d_rows_kernel<real_t, N, G, YT, true, true, PP>;
       if (!occ[1] && (rc = prep(k, smem_rows(true), G * NT, &occ[1]))) return rc;
-      TCFD_LAUNCH(k, grid_for(nblk_rows, occ[1]), G * NT, smem_rows(true), stream, p);
+      TCFD_LAUNCH(k, grid_for(nblk_rows, num_sms, occ[1]), G * NT, smem_rows(true), stream, p);
       break;
     }
+    case TCFD_K_ROWS_EVAL:
     case TCFD_K_ROWS_FWD: {
       auto k = ns2d_rows_kernel<real_t, N, G, YT, true, false, PP>;
       if (!occ[2] && (rc = prep(k, smem_rows(false), G * NT, &occ[2]))) return rc;
-      TCFD_LAUNCH(k, grid_for(nblk_rows, occ[2]), G * NT, smem_rows(false), stream, p);
+      TCFD_LAUNCH(k, grid_for(nblk_rows, num_sms, occ[2]), G * NT, smem_rows(false), stream, p);
       break;
     }
     case TCFD_K_COLS: {
       auto k = ns2d_cols_kernel<real_t, N, GC, PP>;
       if (!occ[3] && (rc = prep(k, smem_cols(), GC * NT, &occ[3]))) return rc;
-      TCFD_LAUNCH(k, grid_for(ntiles, occ[3]), GC * NT, smem_cols(), stream, p);
+      TCFD_LAUNCH(k, grid_for(ntiles, num_sms, occ[3]), GC * NT, smem_cols(), stream, p);
       break;
     }
     default:
       return -1;
   }
+  return 0;
+}
+}  // namespace v1
+#else
+// ------------------------------------------------------------------ second generation (N >= 256)
+namespace v2 {
+constexpr int NTC = NT >= 32 ? NT : 32;  // (only instantiated for N >= 256)
+// resident threads per SM the register budget is tuned for: 512 (fp32: <= 128 regs) / 256 (fp64)
+constexpr int TARGET_THREADS = sizeof(real_t) == 4 ? 512 : 256;
+typedef pack2<real_t>::type lane_t;
+constexpr int MINB_BY_THREADS = (TARGET_THREADS / NTC) > 0 ? (TARGET_THREADS / NTC) : 1;
+// CTAs per SM the shared-memory footprint allows (227 KB usable, 1 KB reserved per CTA)
+constexpr int ROWS_BY_SMEM = (int)(232448 / (RowsSmem<real_t, N>::BYTES + 1024));
+#ifdef TCFD_ROWS3_MINB
+constexpr int MINB_ROWS3 = TCFD_ROWS3_MINB;
+#else
+// one less than shared memory would allow: 168 instead of 128 registers per thread (no spills)
+constexpr int ROWS3_CAP = ROWS_BY_SMEM > 2 ? ROWS_BY_SMEM - 1 : ROWS_BY_SMEM;
+constexpr int MINB_ROWS3 = ROWS3_CAP < 1 ? 1 : (ROWS3_CAP < MINB_BY_THREADS ? ROWS3_CAP : MINB_BY_THREADS);
+#endif
+constexpr int MINB_ROWS = MINB_BY_THREADS;
+constexpr int MINB_COLS = 5;
+constexpr size_t smem_rows() { return (size_t)N * sizeof(cx<lane_t>); }
+constexpr size_t smem_rows3() { return (size_t)RowsSmem<real_t, N>::BYTES; }
+constexpr size_t smem_cols() {
+  return 1024 + (size_t)TileGeom<N / 2 + 1, 4 * (int)sizeof(cx<lane_t>)>::BYTES + (size_t)N * sizeof(cx<lane_t>) + 16;
+}
+
+int launch(int which, const NsParams<real_t>& p, const TileMaps* maps, int num_sms, cudaStream_t stream) {
+  static int occ[7] = {0, 0, 0, 0, 0, 0, 0};
+  const int nunits = p.B * (N / 4 + 1);
+  const int nquads = p.B * (N / 4);
+  int rc = 0;
+  switch (which) {
+    case TCFD_K_ROWS_INV: {
+      auto k = ns2d_rows2_kernel<real_t, N, false, true, ROWS_RK, MINB_ROWS>;
+      if (!occ[0] && (rc = prep(k, smem_rows(), NT, &occ[0]))) return rc;
+      TCFD_LAUNCH(k, grid_for(nunits, num_sms, occ[0]), NT, smem_rows(), stream, p);
+      break;
+    }
+    case TCFD_K_ROWS_FULL: {  // substage: forward rows + update + inverse rows
+      if (p.in_user) {
+        auto k = ns2d_rows3_kernel<real_t, N, true, true, false, MINB_ROWS3>;
+        if (!occ[1] && (rc = prep(k, smem_rows3(), NT, &occ[1]))) return rc;
+        TCFD_LAUNCH(k, grid_for(nunits, num_sms, occ[1]), NT, smem_rows3(), stream, p);
+      } else {
+        auto k = ns2d_rows3_kernel<real_t, N, true, false, false, MINB_ROWS3>;
+        if (!occ[5] && (rc = prep(k, smem_rows3(), NT, &occ[5]))) return rc;
+        TCFD_LAUNCH(k, grid_for(nunits, num_sms, occ[5]), NT, smem_rows3(), stream, p);
+      }
+      break;
+    }
+    case TCFD_K_ROWS_FWD: {  // last substage: forward rows + update, reference layout out
+      if (p.in_user) {
+        auto k = ns2d_rows3_kernel<real_t, N, false, true, true, MINB_ROWS3>;
+        if (!occ[2] && (rc = prep(k, smem_rows3(), NT, &occ[2]))) return rc;
+        TCFD_LAUNCH(k, grid_for(nunits, num_sms, occ[2]), NT, smem_rows3(), stream, p);
+      } else {
+        auto k = ns2d_rows3_kernel<real_t, N, false, false, true, MINB_ROWS3>;
+        if (!occ[6] && (rc = prep(k, smem_rows3(), NT, &occ[6]))) return rc;
+        TCFD_LAUNCH(k, grid_for(nunits, num_sms, occ[6]), NT, smem_rows3(), stream, p);
+      }
+      break;
+    }
+    case TCFD_K_ROWS_EVAL: {
+      auto k = ns2d_rows2_kernel<real_t, N, true, false, ROWS_EVAL, MINB_ROWS>;
+      if (!occ[4] && (rc = prep(k, smem_rows(), NT, &occ[4]))) return rc;
+      TCFD_LAUNCH(k, grid_for(nunits, num_sms, occ[4]), NT, smem_rows(), stream, p);
+      break;
+    }
+    case TCFD_K_COLS: {
+      if (!maps) return -2;
+      auto k = ns2d_cols2_kernel<real_t, N, MINB_COLS>;
+      if (!occ[3] && (rc = prep(k, smem_cols(), NT, &occ[3]))) return rc;
+      TCFD_LAUNCH(k, grid_for(nquads, num_sms, occ[3]), NT, smem_cols(), stream, p, *maps);
+      break;
+    }
+    default:
+      return -1;
+  }
+  return 0;
+}
+}  // namespace v2
+#endif
+
+int launch(int which, const void* params, const void* maps, int num_sms, void* stream_) {
+  const NsParams<real_t>& p = *static_cast<const NsParams<real_t>*>(params);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+#if TCFD_N >= 256
+  rc = v2::launch(which, p, static_cast<const TileMaps*>(maps), num_sms, stream);
+#else
+  (void)maps;
+  rc = v1::launch(which, p, num_sms, stream);
+#endif
+  if (rc) return rc;
 #ifndef TCFD_EMU
   return (int)cudaGetLastError();
 #else
@@ -96,6 +198,11 @@ int launch(int which, const void* params, int num_sms, void* stream_) {
 extern "C" void TCFD_ENTRY(TCFD_PREC, TCFD_N)(tcfd_ns2d_entry_t* e) {
   e->n = N;
   e->prec = TCFD_PREC;
-  e->yt = YT;
+#if TCFD_N < 256
+  e->yt = v1::YT;
+#else
+  e->yt = 4;
+#endif
+  e->v2 = V2 ? 1 : 0;
   e->launch = &launch;
 }

@@ -25,6 +25,12 @@ namespace tcfd {
 
 enum : int { UPD_RK = 0, UPD_F = 1, UPD_RESID = 2 };
 
+// batch-shared tables of one spectrum entry, interleaved (second-generation kernels)
+template <class T>
+struct alignas(4 * sizeof(T)) tab4 {
+  T lin, filt, nil, pad;  // linear_term, 2/3 mask (1 when smooth=False), -1/laplace'
+};
+
 template <class T>
 struct NsParams {
   int B;
@@ -39,6 +45,22 @@ struct NsParams {
   cx<T>* dwdt;
   cx<T>* H;
   cx<T>* advt;
+  // second-generation kernels (ns2d_v2.cuh): packed layouts and the number of advt double rows
+  T* H2;
+  T* advt2;
+  int NDF;
+  const tab4<T>* tab;         // [N][NH]
+  const unsigned char* frow;  // [N] row carries a non-zero forcing entry
+  // unit-layout state between substages and per-d table blocks (ns2d_rows3_kernel)
+  const cx<typename pack2<T>::type>* wU_in;
+  const cx<typename pack2<T>::type>* hU_in;
+  cx<typename pack2<T>::type>* wU_out;
+  cx<typename pack2<T>::type>* hU_out;
+  const void* tabU;            // [ND]{lin[NH][2], nil_a[NH], nil_b[NH]}
+  const unsigned char* maskU;  // [ND][2][MASK_ROW]
+  int in_user, out_user;       // substage reads / writes the reference layout
+  size_t Hplane;               // entries (packed complex) per plane of H2
+  int dbg;                     // timing experiments (only with -DTCFD_DEBUG_KNOBS)
   const cx<T>* tw;
   const T* kappa_x;  // [N]   2 pi kx / N^2
   const T* kappa_y;  // [NH]  2 pi ky / N^2

@@ -1,7 +1,10 @@
 // Internal glue between the per-(precision, N) kernel translation units and ns2d_api.cu.
 #pragma once
-enum { TCFD_K_ROWS_INV = 0, TCFD_K_ROWS_FULL = 1, TCFD_K_ROWS_FWD = 2, TCFD_K_COLS = 3 };
+// ROWS_EVAL: forward rows + F / residual epilogue (explicit_terms, residual); timed kinds are 0..3
+enum { TCFD_K_ROWS_INV = 0, TCFD_K_ROWS_FULL = 1, TCFD_K_ROWS_FWD = 2, TCFD_K_COLS = 3, TCFD_K_ROWS_EVAL = 4 };
 typedef struct {
   int n, prec, yt;
-  int (*launch)(int which, const void* params, int num_sms, void* stream);
+  int v2;  // 1: ns2d_v2.cuh kernels (packed layouts H2/advt2, TMA tile maps), 0: ns2d_kernels.cuh
+  // maps: const tcfd::TileMaps* (v2 cols kernel only, may be null otherwise)
+  int (*launch)(int which, const void* params, const void* maps, int num_sms, void* stream);
 } tcfd_ns2d_entry_t;

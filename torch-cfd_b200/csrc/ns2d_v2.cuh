@@ -1,0 +1,556 @@
+// Second-generation kernels of hot path A for N >= 256 (reference arithmetic: see ns2d_kernels.cuh).
+//
+// What changed with respect to ns2d_kernels.cuh (which still serves N <= 128):
+//  * every FFT runs on a 2-lane type (pack2<T>: f32x2 packed instructions for fp32, a scalar pair
+//    for fp64), so one instruction stream carries two transforms and the exchange moves 16-byte
+//    elements;
+//  * a CTA is ONE FFT group (N/8 threads): CTAs de-synchronise freely, several per SM, and hide
+//    each other's global-memory latency;
+//  * the rows kernel works on a DOUBLE item -- the row pairs (2d, N-2d) and (2d+1, N-2d-1) of one
+//    sample in the two lanes -- for the forward y-FFT and the state update, then runs the inverse
+//    y-FFTs of each item with the lanes (u, dw/dx) and (v, dw/dy);
+//  * the cols kernel takes a QUAD of physical columns: per column ONE packed inverse x-FFT carries
+//    all four fields (lane 0: u + i v, lane 1: dw/dx + i dw/dy), the four advection columns go
+//    through ONE packed forward x-FFT; its input tile (128 bytes of each of the N/2+1 rows kx)
+//    arrives by TMA with the 128B swizzle while the previous quad is still being transformed.
+//
+// Layouts (T = float | double):
+//   H     [B][NH][N][8 T]   entry (kx, y) = { A.x.lo, A.x.hi, A.y.lo, A.y.hi, B.x.lo, ... } with
+//                           A lanes = (u, dw/dx), B lanes = (v, dw/dy) after the y-inverse
+//   advt  [B][ND][N][4 T]   ND = N/4+1 double rows; entry (d, y) = { re_a, re_b, im_a, im_b } of the
+//                           x-transformed advection at rows kx = 2d (a) and 2d+1 (b)
+#pragma once
+#include "ns2d_kernels.cuh"
+#include "tma.cuh"
+
+namespace tcfd {
+
+enum : int { ROWS_RK = 0, ROWS_EVAL = 1 };
+
+// ------------------------------------------------------------------------------------------
+// State update of one spectrum entry in each lane.  `off[l]` is the entry's offset inside one
+// sample (row * NH + col): it addresses the batch-shared tables and, added to the sample base
+// `sb`, the state arrays.  MODE ROWS_RK: the Runge-Kutta/Crank-Nicolson update; ROWS_EVAL: F or
+// the residual (p.mode).  Same operation order as ns_update (ns2d_kernels.cuh).
+template <int MODE, class T, class L>
+TCFD_D cx<L> ns_update2(const NsParams<T>& p, size_t sb, const int (&off)[2], bool forced, cx<L> A,
+                        const bool (&own)[2]) {
+  const tab4<T> t0 = p.tab[off[0]], t1 = p.tab[off[1]];
+  const L f(t0.filt, t1.filt);
+  cx<L> F{f * A.x, f * A.y};
+  if (forced) {
+    const cx<T> f0 = p.fhat[off[0]], f1 = p.fhat[off[1]];
+    F = F + cx<L>{L(f0.x, f1.x), L(f0.y, f1.y)};
+  }
+  const L lin(t0.lin, t1.lin);
+  if constexpr (MODE == ROWS_EVAL) {
+    cx<L> r = F;
+    if (p.mode == UPD_RESID) {
+      const cx<T> w0 = p.w_in[sb + off[0]], w1 = p.w_in[sb + off[1]];
+      const cx<L> w{L(w0.x, w1.x), L(w0.y, w1.y)};
+      const cx<T> u0 = p.w_old[sb + off[0]], u1 = p.w_old[sb + off[1]];
+      const cx<L> wt{L(u0.x, u1.x), L(u0.y, u1.y)};
+      r = (wt - F) - lin * w;
+    }
+    if (own[0]) p.h_out[sb + off[0]] = cx<T>{r.x.lo, r.y.lo};
+    if (own[1]) p.h_out[sb + off[1]] = cx<T>{r.x.hi, r.y.hi};
+    return r;
+  } else {
+    const cx<T> w0 = p.w_in[sb + off[0]], w1 = p.w_in[sb + off[1]];
+    const cx<L> w{L(w0.x, w1.x), L(w0.y, w1.y)};
+    cx<L> h = F;
+    if (p.read_h) {
+      const cx<T> h0 = p.h_in[sb + off[0]], h1 = p.h_in[sb + off[1]];
+      h = F + L(p.beta) * cx<L>{L(h0.x, h1.x), L(h0.y, h1.y)};
+    }
+    if (p.write_h) {
+      if (own[0]) p.h_out[sb + off[0]] = cx<T>{h.x.lo, h.y.lo};
+      if (own[1]) p.h_out[sb + off[1]] = cx<T>{h.x.hi, h.y.hi};
+    }
+    const L inv = L(T(1)) / (L(T(1)) - L(p.mu) * lin);
+    const cx<L> x = (w + L(p.gdt) * h) + L(p.mu) * (lin * w);
+    const cx<L> wn = inv * x;
+    if (own[0]) p.w_out[sb + off[0]] = cx<T>{wn.x.lo, wn.y.lo};
+    if (own[1]) p.w_out[sb + off[1]] = cx<T>{wn.x.hi, wn.y.hi};
+    if (p.dwdt) {
+      if (own[0]) {
+        const cx<T> o = p.w_old[sb + off[0]];
+        p.dwdt[sb + off[0]] = cx<T>{p.inv_tdt * (wn.x.lo - o.x), p.inv_tdt * (wn.y.lo - o.y)};
+      }
+      if (own[1]) {
+        const cx<T> o = p.w_old[sb + off[1]];
+        p.dwdt[sb + off[1]] = cx<T>{p.inv_tdt * (wn.x.hi - o.x), p.inv_tdt * (wn.y.hi - o.y)};
+      }
+    }
+    return wn;
+  }
+}
+
+// Two of the four spectra at one entry, in the lanes:  HALF 0 -> (u, dw/dx) = (i ky psi, i kx w),
+// HALF 1 -> (v, dw/dy) = (-i kx psi, i ky w), with psi = nil * w (nil = -1/lap'), kappa = 2 pi k / N^2.
+template <int HALF, class T>
+TCFD_D cx<typename pack2<T>::type> ns_fields2(cx<T> w, T nil, T kx, T ky) {
+  typedef typename pack2<T>::type L;
+  const L s(nil, T(1));
+  const cx<L> q{s * L(w.x), s * L(w.y)};  // lanes (psi, w)
+  const L c = HALF == 0 ? L(ky, kx) : L(-kx, ky);
+  return cx<L>{-(c * q.y), c * q.x};
+}
+
+template <int LANE, class L>
+TCFD_D cx<typename lane_traits<L>::scalar> lane_of(cx<L> v) {
+  typedef typename lane_traits<L>::scalar T;
+  return LANE ? cx<T>{v.x.hi, v.y.hi} : cx<T>{v.x.lo, v.y.lo};
+}
+
+// y-axis inverse FFT of one half (HALF: lanes (u, dw/dx) or (v, dw/dy)) of the item held in lane
+// LANE of wv (row pair r1, r2 of sample s), written to the H entries of row kx = r1.
+// nil_of(m): -1/laplace' of element m of this item (table in global or shared memory).
+template <int HALF, class T>
+TCFD_D cx<typename pack2<T>::type> ns_fields_s(cx<T> w, T nil, T kx, T ky) {
+  typedef typename pack2<T>::type L;
+  const T px = nil * w.x, py = nil * w.y;  // psi
+  if (HALF == 0) return cx<L>{L(-(ky * py), -(kx * w.y)), L(ky * px, kx * w.x)};
+  return cx<L>{L(kx * py, -(ky * w.y)), L(-(kx * px), ky * w.x)};
+}
+
+template <int LANE, int HALF, class T, int N, class L, class Sync, class NilOf>
+TCFD_D void rows_inverse_half(const NsParams<T>& p, const cx<L> (&wv)[8], cx<L> e0, cx<L> e1, const T (&kyv)[8],
+                              NilOf nil_of, int r1, int r2, T kx1, T kx2, int s, const FftTwiddles<T, N>& tw,
+                              cx<L>* buf, int& parity, int t, Sync& sync) {
+  constexpr int NT = N / 8, NH = N / 2 + 1;
+  cx<L> z[1][8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const bool lo = m < 4;
+    const cx<L> f = ns_fields_s<HALF, T>(lane_of<LANE>(wv[m]), nil_of(m), lo ? kx1 : kx2, kyv[m]);
+    z[0][m] = lo ? f : conj(f);
+  }
+  if (t == 0) {
+    // self-conjugate columns ky = 0 and ky = N/2: Hermitian part of the two rows (C2R semantics)
+    const T ky0 = p.kappa_y[0], kyh = p.kappa_y[N / 2];
+    const cx<L> f1 = ns_fields_s<HALF, T>(lane_of<LANE>(wv[0]), p.tab[r1 * NH].nil, kx1, ky0);
+    const cx<L> f2_ = ns_fields_s<HALF, T>(lane_of<LANE>(e0), p.tab[r2 * NH].nil, kx2, ky0);
+    const cx<L> g1 = ns_fields_s<HALF, T>(lane_of<LANE>(e1), p.tab[r1 * NH + N / 2].nil, kx1, kyh);
+    const cx<L> g2 = ns_fields_s<HALF, T>(lane_of<LANE>(wv[4]), p.tab[r2 * NH + N / 2].nil, kx2, kyh);
+    z[0][0] = L(T(0.5)) * (f1 + conj(f2_));
+    z[0][4] = L(T(0.5)) * (g1 + conj(g2));
+  }
+#ifdef TCFD_DEBUG_KNOBS
+  if (!(p.dbg & 2))
+#endif
+  fft_run<L, N, +1, 1, false, N>(z, tw, buf, parity, t, sync);
+  // plane HALF of H: [sample][kx][y] packed complex -- a warp stores 32 consecutive entries
+  cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + (size_t)HALF * p.Hplane + ((size_t)s * NH + r1) * (size_t)N + t;
+#ifdef TCFD_DEBUG_KNOBS
+  if (p.dbg & 1) {  // timing experiment: keep the values alive without the H traffic
+    T acc = T(0);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc += z[0][m].x.lo + z[0][m].y.hi;
+    if (acc == T(12345.678)) Hrow[0] = z[0][0];
+    return;
+  }
+#endif
+#pragma unroll
+  for (int m = 0; m < 8; ++m) Hrow[m * NT] = z[0][m];
+}
+
+// ------------------------------------------------------------------------------------------
+// rows kernel, generic form: state in the reference layout, tables from global memory.  Used for
+// the prologue (FWD = false: H from the initial state) and for F / residual evaluation
+// (FWD = true, INV = false, MODE = ROWS_EVAL).  CTA = one group, unit = one double item.
+template <class T, int N, bool FWD, bool INV, int MODE, int MINB>
+__global__ void __launch_bounds__(N / 8, MINB)
+ns2d_rows2_kernel(const NsParams<T> p) {
+  typedef typename pack2<T>::type L;
+  constexpr int NT = N / 8, NH = N / 2 + 1, ND = N / 4 + 1;
+  TCFD_DYN_SMEM(smem_raw);
+  cx<L>* buf = reinterpret_cast<cx<L>*>(smem_raw);
+  const int t = threadIdx.x;
+  FftTwiddles<T, N> tw;
+  tw.load(p.tw, t);
+  CtaSync sync;
+  int parity = 0;
+  T kyv[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) kyv[m] = p.kappa_y[m < 4 ? t + m * NT : N - t - m * NT];
+  const int nunits = p.B * ND;
+  const int per = (nunits + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int u_begin = (int)blockIdx.x * per;
+  const int u_end = u_begin + per < nunits ? u_begin + per : nunits;
+
+  for (int unit = u_begin; unit < u_end; ++unit) {
+    const int d = unit / p.B, s = unit % p.B;
+    const size_t sb = (size_t)s * N * NH;
+    // lane 0: rows (2d, N-2d); lane 1: rows (2d+1, N-2d-1), or a copy of lane 0 past the Nyquist row
+    const bool valid1 = 2 * d + 1 <= N / 2;
+    const int r1a = 2 * d, r2a = (N - r1a) % N;
+    const int r1b = valid1 ? 2 * d + 1 : r1a, r2b = (N - r1b) % N;
+    const bool selfa = r1a == r2a, selfb = r1b == r2b;
+    const T kx1a = p.kappa_x[r1a], kx2a = p.kappa_x[r2a], kx1b = p.kappa_x[r1b], kx2b = p.kappa_x[r2b];
+    const int lo_a = r1a * NH + t, hi_a = r2a * NH + N - t, lo_b = r1b * NH + t, hi_b = r2b * NH + N - t;
+    cx<L> wv[8], e0, e1;  // e0 = entries (r2, 0), e1 = entries (r1, N/2): owned by thread 0
+
+    if constexpr (FWD) {
+      const bool forced = p.fhat && (p.frow[r1a] | p.frow[r2a] | p.frow[r1b] | p.frow[r2b]);
+      cx<L> a[1][8];
+      if (d < p.NDF) {
+        const cx<L>* src = reinterpret_cast<const cx<L>*>(p.advt2) + ((size_t)s * ND + d) * N + t;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) a[0][m] = src[m * NT];
+        fft_run<L, N, -1, 1, false, N>(a, tw, buf, parity, t, sync);
+      } else {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) a[0][m] = cx<L>{L(T(0)), L(T(0))};
+      }
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const bool lo = m < 4;
+        const int off[2] = {lo ? lo_a + m * NT : hi_a - m * NT, lo ? lo_b + m * NT : hi_b - m * NT};
+        const bool own[2] = {lo || !selfa || (m == 4 && t == 0), valid1 && (lo || !selfb || (m == 4 && t == 0))};
+        wv[m] = ns_update2<MODE, T, L>(p, sb, off, forced, lo ? a[0][m] : conj(a[0][m]), own);
+      }
+      if (t == 0) {
+        const bool own[2] = {!selfa, valid1 && !selfb};
+        const int off0[2] = {r2a * NH, r2b * NH};
+        e0 = ns_update2<MODE, T, L>(p, sb, off0, forced, conj(a[0][0]), own);
+        const int off1[2] = {r1a * NH + N / 2, r1b * NH + N / 2};
+        e1 = ns_update2<MODE, T, L>(p, sb, off1, forced, a[0][4], own);
+      }
+    } else {
+      const cx<T>* w = p.w_in + sb;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const bool lo = m < 4;
+        const cx<T> w0 = w[lo ? lo_a + m * NT : hi_a - m * NT], w1 = w[lo ? lo_b + m * NT : hi_b - m * NT];
+        wv[m] = cx<L>{L(w0.x, w1.x), L(w0.y, w1.y)};
+      }
+      if (t == 0) {
+        const cx<T> a0 = w[r2a * NH], a1 = w[r2b * NH];
+        e0 = cx<L>{L(a0.x, a1.x), L(a0.y, a1.y)};
+        const cx<T> b0 = w[r1a * NH + N / 2], b1 = w[r1b * NH + N / 2];
+        e1 = cx<L>{L(b0.x, b1.x), L(b0.y, b1.y)};
+      }
+    }
+
+    if constexpr (INV) {
+      auto nil_a = [&](int m) { return p.tab[m < 4 ? lo_a + m * NT : hi_a - m * NT].nil; };
+      auto nil_b = [&](int m) { return p.tab[m < 4 ? lo_b + m * NT : hi_b - m * NT].nil; };
+      rows_inverse_half<0, 0, T, N>(p, wv, e0, e1, kyv, nil_a, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
+      rows_inverse_half<0, 1, T, N>(p, wv, e0, e1, kyv, nil_a, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
+      if (valid1) {  // CTA-uniform
+        rows_inverse_half<1, 0, T, N>(p, wv, e0, e1, kyv, nil_b, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
+        rows_inverse_half<1, 1, T, N>(p, wv, e0, e1, kyv, nil_b, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// rows kernel, substage form (forward y-FFT + RK/CN update [+ inverse y-FFTs]).
+//
+// Between substages the state lives in the UNIT layout: for unit (s, d) one contiguous block
+//   U[s][d][half][col] = { re_a, re_b, im_a, im_b }      half 0: rows r1 = (2d, 2d+1)
+//                                                         half 1: rows r2 = (N-2d, N-2d-1)
+// i.e. exactly what the unit reads and writes, lanes already interleaved: one 1-D bulk copy (TMA
+// engine, no registers, no LSU issue) stages a unit's w and h while the previous unit is still in
+// its inverse transforms, and every access is one 16-byte LDS / STG.  Self-conjugate rows keep an
+// independent copy of their mirrored half.  IN_USER / OUT_USER: the first / last substage of a call
+// reads / writes the reference layout instead.
+// Tables come from per-d blocks staged the same way whenever d changes:
+//   tabU[d] = { lin[col] = (lin_a, lin_b) ; nil_a[col] ; nil_b[col] }  (the tables are even in kx:
+//   one copy serves both halves), maskU[d][half][col] = bit 0: lane a kept, bit 1: lane b kept.
+template <class T, int N>
+struct RowsSmem {
+  typedef typename pack2<T>::type L;
+  static constexpr int NH = N / 2 + 1;
+  static constexpr int ENT = (int)sizeof(cx<L>);
+  static constexpr int UNIT_BYTES = 2 * NH * ENT;
+  static constexpr int TAB_BYTES = (NH * 4 * (int)sizeof(T) + 15) / 16 * 16;
+  static constexpr int MASK_ROW = (NH + 15) / 16 * 16;
+  static constexpr int OFF_BUF = 0;
+  static constexpr int OFF_W = OFF_BUF + N * ENT;
+  static constexpr int OFF_H = OFF_W + UNIT_BYTES;
+  static constexpr int OFF_TAB = OFF_H + UNIT_BYTES;
+  static constexpr int OFF_MASK = OFF_TAB + TAB_BYTES;
+  static constexpr int OFF_BAR = OFF_MASK + 2 * MASK_ROW;
+  static constexpr int BYTES = OFF_BAR + 16;
+};
+
+template <class T, int N, bool INV, bool IN_USER, bool OUT_USER, int MINB>
+__global__ void __launch_bounds__(N / 8, MINB)
+ns2d_rows3_kernel(const NsParams<T> p) {
+  typedef typename pack2<T>::type L;
+  typedef RowsSmem<T, N> S;
+  constexpr int NT = N / 8, NH = N / 2 + 1, ND = N / 4 + 1;
+  TCFD_DYN_SMEM(smem_raw);
+  cx<L>* buf = reinterpret_cast<cx<L>*>(smem_raw + S::OFF_BUF);
+  const cx<L>* wst = reinterpret_cast<const cx<L>*>(smem_raw + S::OFF_W);
+  const cx<L>* hst = reinterpret_cast<const cx<L>*>(smem_raw + S::OFF_H);
+  // table block: lin[NH] (both lanes), nil_a[NH], nil_b[NH] -- separate planes, unit-stride reads
+  const L* linst = reinterpret_cast<const L*>(smem_raw + S::OFF_TAB);
+  const T* nilst = reinterpret_cast<const T*>(smem_raw + S::OFF_TAB) + 2 * NH;
+  const unsigned char* maskst = smem_raw + S::OFF_MASK;
+  unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + S::OFF_BAR);
+  unsigned long long* bar_t = bar_s + 1;
+  const int t = threadIdx.x;
+  FftTwiddles<T, N> tw;
+  tw.load(p.tw, t);
+  CtaSync sync;
+  int parity = 0;
+  T kyv[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) kyv[m] = p.kappa_y[m < 4 ? t + m * NT : N - t - m * NT];
+  const int nunits = p.B * ND;
+  const int per = (nunits + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int u_begin = (int)blockIdx.x * per;
+  const int u_end = u_begin + per < nunits ? u_begin + per : nunits;
+  const bool stage_w = !IN_USER, stage_h = p.read_h != 0;
+  const bool stage_any = stage_w || stage_h;
+
+  auto issue_state = [&](int unit) {  // one thread
+    const int d = unit / p.B, s = unit % p.B;
+    const size_t blk = ((size_t)s * ND + d) * 2 * NH;
+    stage_expect(bar_s, (unsigned)S::UNIT_BYTES * ((stage_w ? 1u : 0u) + (stage_h ? 1u : 0u)));
+    if (stage_w) bulk_load(smem_raw + S::OFF_W, p.wU_in + blk, (unsigned)S::UNIT_BYTES, bar_s);
+    if (stage_h) bulk_load(smem_raw + S::OFF_H, p.hU_in + blk, (unsigned)S::UNIT_BYTES, bar_s);
+  };
+  auto issue_table = [&](int d) {  // one thread
+    stage_expect(bar_t, (unsigned)(S::TAB_BYTES + 2 * S::MASK_ROW));
+    bulk_load(smem_raw + S::OFF_TAB, reinterpret_cast<const unsigned char*>(p.tabU) + (size_t)d * S::TAB_BYTES,
+              (unsigned)S::TAB_BYTES, bar_t);
+    bulk_load(smem_raw + S::OFF_MASK, p.maskU + (size_t)d * 2 * S::MASK_ROW, (unsigned)(2 * S::MASK_ROW), bar_t);
+  };
+  if (t == 0) {
+    stage_barrier_init(bar_s);
+    stage_barrier_init(bar_t);
+  }
+  __syncthreads();
+  if (t == 0 && u_begin < u_end) {
+    issue_table(u_begin / p.B);
+    if (stage_any) issue_state(u_begin);
+  }
+  unsigned phase_s = 0, phase_t = 0;
+  int d_have = -1;
+
+  for (int unit = u_begin; unit < u_end; ++unit) {
+    const int d = unit / p.B, s = unit % p.B;
+    const size_t sb = (size_t)s * N * NH;               // reference layout: sample base
+    const size_t ub = ((size_t)s * ND + d) * 2 * NH;    // unit layout: block base
+    const bool valid1 = 2 * d + 1 <= N / 2;
+    const int r1a = 2 * d, r2a = (N - r1a) % N;
+    const int r1b = valid1 ? 2 * d + 1 : r1a, r2b = (N - r1b) % N;
+    const bool selfa = r1a == r2a, selfb = r1b == r2b;
+    const T kx1a = p.kappa_x[r1a], kx2a = p.kappa_x[r2a], kx1b = p.kappa_x[r1b], kx2b = p.kappa_x[r2b];
+    const bool forced = p.fhat && (p.frow[r1a] | p.frow[r2a] | p.frow[r1b] | p.frow[r2b]);
+    cx<L> wv[8], e0, e1;
+
+    cx<L> a[1][8];
+    const bool adv = d < p.NDF;
+    if (adv) {
+      const cx<L>* src = reinterpret_cast<const cx<L>*>(p.advt2) + ((size_t)s * ND + d) * N + t;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) a[0][m] = src[m * NT];
+    }
+    if (d != d_have) {  // CTA-uniform
+      tile_load_wait(bar_t, phase_t);
+      phase_t ^= 1u;
+      d_have = d;
+    }
+    if (adv) {
+      fft_run<L, N, -1, 1, false, N>(a, tw, buf, parity, t, sync);
+    } else {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) a[0][m] = cx<L>{L(T(0)), L(T(0))};
+    }
+    if (stage_any) {
+      tile_load_wait(bar_s, phase_s);
+      phase_s ^= 1u;
+    }
+
+    // RK / CN update of entry (half, col) in both lanes; returns the new w
+    auto update = [&](int half, int col, cx<L> A, bool own_a, bool own_b) -> cx<L> {
+      const int ra = half ? r2a : r1a, rb = half ? r2b : r1b;
+      const L lin = linst[col];
+      const unsigned mk = maskst[half * S::MASK_ROW + col];
+      const L f((mk & 1u) ? T(1) : T(0), (mk & 2u) ? T(1) : T(0));
+      cx<L> F{f * A.x, f * A.y};
+      if (forced) {
+        const cx<T> f0 = p.fhat[ra * NH + col], f1 = p.fhat[rb * NH + col];
+        F = F + cx<L>{L(f0.x, f1.x), L(f0.y, f1.y)};
+      }
+      cx<L> w;
+      if constexpr (IN_USER) {
+        const cx<T> w0 = p.w_in[sb + ra * NH + col], w1 = p.w_in[sb + rb * NH + col];
+        w = cx<L>{L(w0.x, w1.x), L(w0.y, w1.y)};
+      } else {
+        w = wst[half * NH + col];
+      }
+      cx<L> h = F;
+      if (p.read_h) h = F + L(p.beta) * hst[half * NH + col];
+      if (p.write_h) p.hU_out[ub + half * NH + col] = h;
+      const L den = L(T(1)) - L(p.mu) * lin;
+      const L inv(rcp_rn(den.lo), rcp_rn(den.hi));
+      const cx<L> x = (w + L(p.gdt) * h) + L(p.mu) * (lin * w);
+      const cx<L> wn = inv * x;
+      if constexpr (OUT_USER) {
+        if (own_a) p.w_out[sb + ra * NH + col] = cx<T>{wn.x.lo, wn.y.lo};
+        if (own_b) p.w_out[sb + rb * NH + col] = cx<T>{wn.x.hi, wn.y.hi};
+        if (p.dwdt) {
+          if (own_a) {
+            const cx<T> o = p.w_old[sb + ra * NH + col];
+            p.dwdt[sb + ra * NH + col] = cx<T>{p.inv_tdt * (wn.x.lo - o.x), p.inv_tdt * (wn.y.lo - o.y)};
+          }
+          if (own_b) {
+            const cx<T> o = p.w_old[sb + rb * NH + col];
+            p.dwdt[sb + rb * NH + col] = cx<T>{p.inv_tdt * (wn.x.hi - o.x), p.inv_tdt * (wn.y.hi - o.y)};
+          }
+        }
+      } else {
+        p.wU_out[ub + half * NH + col] = wn;
+      }
+      return wn;
+    };
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const bool lo = m < 4;
+      const int col = lo ? t + m * NT : N - t - m * NT;
+      const bool first = lo || (m == 4 && t == 0);
+      wv[m] = update(lo ? 0 : 1, col, lo ? a[0][m] : conj(a[0][m]), first || !selfa, valid1 && (first || !selfb));
+    }
+    if (t == 0) {
+      e0 = update(1, 0, conj(a[0][0]), !selfa, valid1 && !selfb);
+      e1 = update(0, N / 2, a[0][4], !selfa, valid1 && !selfb);
+    }
+    if (stage_any) {
+      // the state stage is consumed: start the next unit's copies under this unit's inverse transforms
+      __syncthreads();
+      if (t == 0 && unit + 1 < u_end) issue_state(unit + 1);
+    }
+
+    if constexpr (INV) {
+      auto nil_a = [&](int m) { return nilst[m < 4 ? t + m * NT : N - t - m * NT]; };
+      auto nil_b = [&](int m) { return nilst[NH + (m < 4 ? t + m * NT : N - t - m * NT)]; };
+      rows_inverse_half<0, 0, T, N>(p, wv, e0, e1, kyv, nil_a, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
+      rows_inverse_half<0, 1, T, N>(p, wv, e0, e1, kyv, nil_a, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
+      if (valid1) {  // CTA-uniform
+        rows_inverse_half<1, 0, T, N>(p, wv, e0, e1, kyv, nil_b, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
+        rows_inverse_half<1, 1, T, N>(p, wv, e0, e1, kyv, nil_b, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
+      }
+    }
+    if (unit + 1 < u_end && (unit + 1) / p.B != d) {  // CTA-uniform: the next unit needs another table block
+      __syncthreads();
+      if (t == 0) issue_table((unit + 1) / p.B);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// cols kernel: CTA = one group, unit = one quad of physical columns of one sample.
+template <class T, class G>
+TCFD_D cx<typename pack2<T>::type> tile_ld(const unsigned char* tile, int row, int plane, int c) {
+  typedef typename pack2<T>::type L;
+  if (sizeof(T) == 4) return *reinterpret_cast<const cx<L>*>(tile + G::chunk_offset(row, plane, c));
+  cx<L> r;
+  r.x = *reinterpret_cast<const L*>(tile + G::chunk_offset(row, plane, 2 * c));
+  r.y = *reinterpret_cast<const L*>(tile + G::chunk_offset(row, plane, 2 * c + 1));
+  return r;
+}
+
+template <class T, int N, int MINB>
+__global__ void __launch_bounds__(N / 8, MINB)
+ns2d_cols2_kernel(const NsParams<T> p, const
+#ifndef TCFD_EMU
+                  __grid_constant__
+#endif
+                  TileMaps maps) {
+  typedef typename pack2<T>::type L;
+  constexpr int NT = N / 8, NH = N / 2 + 1, ND = N / 4 + 1;
+  constexpr int IB = 4 * (int)sizeof(cx<L>);  // inner box: 4 columns of one plane (64 or 128 bytes)
+  typedef TileGeom<NH, IB> G;
+  TCFD_DYN_SMEM(smem_raw);
+  // hardware swizzle: the tile must start on a 1 KB boundary (offset arithmetic keeps the pointer
+  // in the shared address space, so the accesses compile to LDS/STS)
+  unsigned char* tile = smem_raw + ((1024u - (smem_offset(smem_raw) & 1023u)) & 1023u);
+  cx<L>* buf = reinterpret_cast<cx<L>*>(tile + G::BYTES);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(buf + N);
+  const int t = threadIdx.x;
+  FftTwiddles<T, N> tw;
+  tw.load(p.tw, t);
+  CtaSync sync;
+  int parity = 0;
+  const int nquads = p.B * (N / 4);
+  const int my_quads = ((int)blockIdx.x < nquads) ? (nquads - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  auto issue = [&](int j) {  // quad j of this CTA's sequence
+    const int quad = (int)blockIdx.x + j * (int)gridDim.x;
+    tile_load_issue<NH, IB>(tile, maps, (quad % (N / 4)) * 4, quad / (N / 4), bar);
+  };
+#ifndef TCFD_EMU
+  if (t == 0) {
+    mbar_init(bar, 1);
+    tma_prefetch_desc(&maps.main);
+    tma_prefetch_desc(&maps.last);
+  }
+#endif
+  __syncthreads();
+  if (t == 0 && my_quads > 0) issue(0);
+  unsigned phase = 0;  // mbarrier parity
+
+  for (int qi = 0; qi < my_quads; ++qi) {
+    const int quad = (int)blockIdx.x + qi * (int)gridDim.x;
+    const int s = quad / (N / 4), y0 = (quad % (N / 4)) * 4;
+    cx<L> cc[1][8];
+    tile_load_wait(bar, phase);
+    phase ^= 1u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      cx<L> z[1][8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int k = t + m * NT;
+        const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
+        const int row = lo ? k : N - k;
+        const cx<L> A = tile_ld<T, G>(tile, row, 0, c);
+        const cx<L> Bv = tile_ld<T, G>(tile, row, 1, c);
+        z[0][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
+        if ((m == 0 || m == 4) && t == 0) z[0][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
+      }
+      fft_run<L, N, +1, 1, false, N>(z, tw, buf, parity, t, sync);
+      if (c == 3) {
+        // every thread has passed a barrier after consuming its tile reads: the tile is free
+        if (t == 0 && qi + 1 < my_quads) issue(qi + 1);
+      }
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const T adv = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
+        if (c == 0) cc[0][m].x.lo = adv;
+        if (c == 1) cc[0][m].y.lo = adv;
+        if (c == 2) cc[0][m].x.hi = adv;
+        if (c == 3) cc[0][m].y.hi = adv;
+      }
+    }
+    fft_run<L, N, -1, 1, false, N>(cc, tw, buf, parity, t, sync);
+    // separate the four real columns (lane lo: columns 0,1; lane hi: columns 2,3) and write the
+    // double rows that carry unmasked modes
+#pragma unroll
+    for (int m = 0; m < 8; ++m) buf[t + m * NT] = cc[0][m];
+    __syncthreads();
+    cx<L>* dst = reinterpret_cast<cx<L>*>(p.advt2) + (size_t)s * ND * N + y0;
+    for (int j = t; j < p.NDF; j += NT) {
+      const int k = 2 * j;
+      const cx<L> c0 = buf[k], c1 = buf[k + 1], n0 = buf[(N - k) % N], n1 = buf[N - k - 1];
+      const L hf(T(0.5));
+      const L Ea = hf * (c0.x + n0.x), Fa = hf * (c0.y - n0.y), Ga = hf * (c0.y + n0.y), Ha = hf * (n0.x - c0.x);
+      const L Eb = hf * (c1.x + n1.x), Fb = hf * (c1.y - n1.y), Gb = hf * (c1.y + n1.y), Hb = hf * (n1.x - c1.x);
+      cx<L>* o = dst + (size_t)j * N;
+      o[0] = cx<L>{L(Ea.lo, Eb.lo), L(Fa.lo, Fb.lo)};
+      o[1] = cx<L>{L(Ga.lo, Gb.lo), L(Ha.lo, Hb.lo)};
+      o[2] = cx<L>{L(Ea.hi, Eb.hi), L(Fa.hi, Fb.hi)};
+      o[3] = cx<L>{L(Ga.hi, Gb.hi), L(Ha.hi, Hb.hi)};
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace tcfd

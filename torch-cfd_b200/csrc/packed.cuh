@@ -61,8 +61,33 @@ TCFD_D f2 operator*(f2 a, float s) { return a * f2(s); }
 TCFD_D f2 operator*(float s, f2 a) { return a * f2(s); }
 TCFD_D f2 fma_rn(f2 a, float s, f2 c) { return fma_rn(a, f2(s), c); }
 
+TCFD_D f2 operator/(f2 a, f2 b) { return f2(a.lo / b.lo, a.hi / b.hi); }  // IEEE div.rn per lane
+
+// The fp64 counterpart: two doubles handled by scalar instructions (sm_100a has no packed fp64
+// arithmetic); same interface, so the kernels are written once over a 2-lane type.
+struct alignas(16) d2 {
+  double lo, hi;
+  d2() = default;
+  TCFD_HD d2(double a, double b) : lo(a), hi(b) {}
+  TCFD_HD explicit d2(double s) : lo(s), hi(s) {}
+};
+TCFD_HD d2 operator+(d2 a, d2 b) { return d2(a.lo + b.lo, a.hi + b.hi); }
+TCFD_HD d2 operator-(d2 a, d2 b) { return d2(a.lo - b.lo, a.hi - b.hi); }
+TCFD_HD d2 operator*(d2 a, d2 b) { return d2(a.lo * b.lo, a.hi * b.hi); }
+TCFD_HD d2 operator/(d2 a, d2 b) { return d2(a.lo / b.lo, a.hi / b.hi); }
+TCFD_HD d2 operator-(d2 a) { return d2(-a.lo, -a.hi); }
+TCFD_HD d2 fma_rn(d2 a, d2 b, d2 c) { return d2(fma(a.lo, b.lo, c.lo), fma(a.hi, b.hi, c.hi)); }
+TCFD_HD d2 operator*(d2 a, double s) { return a * d2(s); }
+TCFD_HD d2 operator*(double s, d2 a) { return a * d2(s); }
+TCFD_HD d2 fma_rn(d2 a, double s, d2 c) { return fma_rn(a, d2(s), c); }
+
 // scalar type behind a lane type (tables, twiddles)
 template <class T> struct lane_traits { typedef T scalar; static constexpr int width = 1; };
 template <> struct lane_traits<f2> { typedef float scalar; static constexpr int width = 2; };
+template <> struct lane_traits<d2> { typedef double scalar; static constexpr int width = 2; };
+// the 2-lane type of a scalar type
+template <class T> struct pack2;
+template <> struct pack2<float> { typedef f2 type; };
+template <> struct pack2<double> { typedef d2 type; };
 
 }  // namespace tcfd

@@ -27,4 +27,13 @@ template <class T> TCFD_D cx<T> conj(cx<T> a) { return cx<T>{a.x, -a.y}; }
 TCFD_HD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
 TCFD_HD double fma_rn(double a, double b, double c) { return fma(a, b, c); }
 
+// correctly rounded reciprocal (== 1/x in IEEE arithmetic, without the generic division's slow path)
+#ifndef TCFD_EMU
+TCFD_D float rcp_rn(float x) { return __frcp_rn(x); }
+TCFD_D double rcp_rn(double x) { return __drcp_rn(x); }
+#else
+TCFD_D float rcp_rn(float x) { return 1.0f / x; }
+TCFD_D double rcp_rn(double x) { return 1.0 / x; }
+#endif
+
 }  // namespace tcfd

@@ -52,8 +52,8 @@ inline void __syncthreads() { emu_barrier.wait(); }
 
 template <class F>
 inline void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, F&& body) {
-  std::vector<unsigned char> smem(smem_bytes + 64);
-  emu_smem_ptr = smem.data();
+  std::vector<unsigned char> smem(smem_bytes + 1024 + 64);
+  emu_smem_ptr = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 1023) & ~(uintptr_t)1023);
   blockDim.x = block;
   gridDim.x = grid;
   emu_barrier.reset(block);
@@ -81,7 +81,10 @@ inline void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, F&& bod
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 #define cudaSuccess 0
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
+inline cudaError_t cudaMalloc(void** p, size_t n) {  // 256-byte aligned like the device allocator
+  *p = std::aligned_alloc(256, ((n ? n : 1) + 255) / 256 * 256);
+  return *p ? 0 : 2;
+}
 inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
 enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { std::memcpy(d, s, n); return 0; }

@@ -1,0 +1,173 @@
+// TMA (cp.async.bulk.tensor) + mbarrier wrappers used by the cols kernel to pull a strided
+// [kx][TC columns] tile of H into shared memory asynchronously (SASS: UTMALDG + SYNCS), with the
+// hardware 128-byte swizzle so that the column reads that follow are bank-conflict free.
+// Under TCFD_EMU the same interface is a synchronous strided copy that applies the same swizzle.
+#pragma once
+#include "tcfd_common.cuh"
+
+#ifndef TCFD_EMU
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
+
+namespace tcfd {
+
+// The H tile source.  H is stored as two planes (A: lanes (u, dw/dx), B: lanes (v, dw/dy)), each
+// [sample][kx][y] entries of one packed complex (ENT bytes).  A tile is, for every row kx of one
+// sample, the 4 entries of 4 consecutive columns y in both planes.
+#ifndef TCFD_EMU
+struct alignas(64) TileMaps {
+  CUtensorMap main;  // rank 4, box {4 entries, min(256, NH-1) rows, 1 sample, 2 planes}
+  CUtensorMap last;  // rank 4, box {4 entries, 1 row, 1 sample, 2 planes}: the Nyquist row kx = N/2
+};
+#else
+struct TileMaps {
+  const unsigned char* base;
+  size_t row_bytes, sample_bytes, plane_bytes;
+};
+#endif
+
+// Shared-memory image of a tile with NH rows whose inner box is IB = 64 or 128 bytes (hardware
+// swizzle of the same width).  Rows [0, NH-1) arrive in boxes of BOX rows x 2 planes, stored
+// [box][plane][row][IB]; the last row's two planes follow.  tile_entry_offset returns the byte
+// offset of 16-byte chunk j of (row, plane) -- the swizzle XORs the chunk index with address bits
+// 7.. (the tile base is 1 KB aligned, so offsets and addresses agree in those bits).
+template <int NH, int IB>
+struct TileGeom {
+  static constexpr int BOX = (NH - 1) < 256 ? (NH - 1) : 256;
+  static constexpr int NBOX = (NH - 1) / BOX;
+  static constexpr int BYTES = ((NH * 2 * IB) + 1023) / 1024 * 1024;
+  static constexpr int XMASK = IB / 16 - 1;  // 3 (64B swizzle) or 7 (128B swizzle)
+  TCFD_HD static int row_offset(int row, int plane) {
+    if (row < NH - 1) return ((row / BOX) * 2 + plane) * (BOX * IB) + (row % BOX) * IB;
+    return NBOX * 2 * BOX * IB + plane * IB;
+  }
+  TCFD_HD static int chunk_offset(int row, int plane, int j) {
+    const int ro = row_offset(row, plane);
+    return ro + ((j ^ ((ro >> 7) & XMASK)) << 4);
+  }
+};
+
+// offset of a shared-memory pointer inside the CTA's shared window
+TCFD_D unsigned smem_offset(const void* p) {
+#ifndef TCFD_EMU
+  return (unsigned)__cvta_generic_to_shared(p);
+#else
+  return (unsigned)(reinterpret_cast<uintptr_t>(p) & 0xffffffffu);
+#endif
+}
+
+#ifndef TCFD_EMU
+TCFD_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+TCFD_D void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+TCFD_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// Spin on the phase; bounded by the SM clock (about 2 s) so that a lost transaction traps instead of
+// hanging the GPU.
+TCFD_D void mbar_wait(unsigned long long* bar, unsigned phase) {
+  const unsigned addr = smem_u32(bar);
+  unsigned done = 0;
+  long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(phase)
+        : "memory");
+    if (done) return;
+    if (spin == 64) t0 = clock64();
+    if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) asm volatile("trap;");
+  }
+}
+TCFD_D void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+TCFD_D void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+TCFD_D void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(map)) : "memory");
+}
+#endif
+
+// 1-D bulk copy global -> shared (SASS: UBLKCP); src, dst and bytes multiples of 16.  The caller
+// announces the total byte count of all copies of a stage with stage_expect().
+TCFD_D void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+#ifndef TCFD_EMU
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+#else
+  (void)bar;
+  std::memcpy(dst, src, bytes);
+#endif
+}
+TCFD_D void stage_expect(unsigned long long* bar, unsigned bytes) {
+#ifndef TCFD_EMU
+  mbar_expect_tx(bar, bytes);
+#else
+  (void)bar;
+  (void)bytes;
+#endif
+}
+TCFD_D void stage_barrier_init(unsigned long long* bar) {
+#ifndef TCFD_EMU
+  mbar_init(bar, 1);
+#else
+  (void)bar;
+#endif
+}
+
+// Issue the load of one tile (called by ONE thread): columns y0..y0+3 of `sample`.
+// elems_per_entry = reals per packed complex entry (4).
+template <int NH, int IB>
+TCFD_D void tile_load_issue(unsigned char* tile, const TileMaps& maps, int y0, int sample, unsigned long long* bar) {
+  typedef TileGeom<NH, IB> G;
+#ifndef TCFD_EMU
+  mbar_expect_tx(bar, (unsigned)NH * 2u * (unsigned)IB);
+  const int c0 = y0 * 4;  // innermost coordinate in reals: 4 reals per entry
+#pragma unroll
+  for (int b = 0; b < G::NBOX; ++b)
+    tma_load_4d(tile + b * 2 * G::BOX * IB, &maps.main, c0, b * G::BOX, sample, 0, bar);
+  tma_load_4d(tile + G::NBOX * 2 * G::BOX * IB, &maps.last, c0, NH - 1, sample, 0, bar);
+#else
+  (void)bar;
+  const int ent = IB / 4;  // bytes per entry
+  for (int pl = 0; pl < 2; ++pl)
+    for (int r = 0; r < NH; ++r) {
+      const unsigned char* src = maps.base + (size_t)pl * maps.plane_bytes + (size_t)sample * maps.sample_bytes +
+                                 (size_t)r * maps.row_bytes + (size_t)y0 * ent;
+      for (int j = 0; j < IB / 16; ++j) std::memcpy(tile + G::chunk_offset(r, pl, j), src + 16 * j, 16);
+    }
+#endif
+}
+
+// All threads of the CTA wait for the tile whose load was issued with `bar` (phase = parity of
+// the number of tiles consumed so far on this barrier).
+TCFD_D void tile_load_wait(unsigned long long* bar, unsigned phase) {
+#ifndef TCFD_EMU
+  mbar_wait(bar, phase);
+#else
+  (void)bar;
+  (void)phase;
+  __syncthreads();  // the emulated load is a plain copy by one host thread
+#endif
+}
+
+}  // namespace tcfd
