@@ -105,6 +105,52 @@ int tcfd_ns2d_step_host(tcfd_ns2d_t* h, const void* w_in_host, void* w_out_host,
                         int batch, int steps, int nstages, const double* beta, const double* gdt,
                         const double* mu, double inv_total_dt, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Hot path B: FNO3d / SFNO spectral convolution  y = irfftn( W (.) rfftn(x) )  on the four retained
+ * corner blocks, fp32.
+ * Replaces: SpectralConv3d.forward (fno/fno3d.py:86-116), SpectralConv.forward (fno/base.py:229-237)
+ *           with SpectralConvS.spectral_conv (fno/sfno.py:364-391), SpectralConvT.forward
+ *           (fno/sfno.py:433-457, postprocess = Identity), and their autograd backward.
+ *   x        [batch][Ci][X][Y][T_in]  float, device           (time innermost, as the reference)
+ *   y        [batch][Co][X][Y][T_out] float, device
+ *   w[4]     four device pointers, each [Ci][Co][mx][my][mt] complex64: weights1..4 of SpectralConv3d
+ *            = view_as_complex(weight[0..3]) of SpectralConvS -- corner order (lo x, lo y),
+ *            (hi x, lo y), (lo x, hi y), (hi x, hi y)
+ *   bias[4]  NULL or four device pointers [mx][my][mt] complex64; delta * bias is added to every
+ *            (batch, out-channel) entry of the corner (fno/sfno.py:386-388)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tcfd_sconv3d tcfd_sconv3d_t;
+
+typedef struct {
+  int X, Y;      /* spatial grid: powers of two in [32, 512] */
+  int T_in;      /* time samples of x */
+  int t_pad;     /* zeros prepended in time before the transform (SpectralConvT temporal_padding), else 0 */
+  int T_out;     /* time samples of y: irfftn(s=(X, Y, T_out + t_pad)) keeping the last T_out */
+  int Ci, Co;
+  int mx, my, mt; /* retained modes: mx <= X/2, my <= Y/2, mt <= (T_in + t_pad)/2 + 1 */
+  int norm;      /* 0 "backward" (torch default), 1 "ortho", 2 "forward" */
+  int max_batch;
+} tcfd_sconv3d_desc_t;
+
+int tcfd_sconv3d_create(tcfd_sconv3d_t** out, const tcfd_sconv3d_desc_t* desc);
+int tcfd_sconv3d_destroy(tcfd_sconv3d_t* h);
+size_t tcfd_sconv3d_workspace_bytes(const tcfd_sconv3d_t* h);
+/* complex64 elements of the truncated input spectrum saved for backward: batch * Ci * 4 mx my mt */
+size_t tcfd_sconv3d_xhat_elems(const tcfd_sconv3d_t* h, int batch);
+int tcfd_sconv3d_last_launch_count(const tcfd_sconv3d_t* h);
+
+/* forward; xhat_save (device, tcfd_sconv3d_xhat_elems complex64) may be NULL when no backward follows */
+int tcfd_sconv3d_forward(tcfd_sconv3d_t* h, const void* x, const void* const* w, const void* const* bias,
+                         float delta, void* y, void* xhat_save, int batch, void* stream);
+
+/* backward of the above for a cotangent grad_y [batch][Co][X][Y][T_out]:
+ *   grad_x   [batch][Ci][X][Y][T_in] or NULL
+ *   grad_w   NULL or four pointers shaped like w        (torch convention: sum_b conj(x_hat) g_hat)
+ *   grad_bias NULL or four pointers shaped like bias    (delta * sum over batch and out-channels) */
+int tcfd_sconv3d_backward(tcfd_sconv3d_t* h, const void* grad_y, const void* xhat, const void* const* w,
+                          void* grad_x, void* const* grad_w, void* const* grad_bias, float delta, int batch,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,7 +106,9 @@ def mask_case():
     print("mask", {k: v.tolist() for k, v in out.items() if k.startswith("n")})
 
 
-def sconv_cases():
+def sconv_cases(grid32=False):
+    """grid32=False: tiny grids (oracle pinning); grid32=True: 32-point grids, the smallest the CUDA
+    kernels serve, written to sconv32.npz so the kernel path is checked against the reference itself."""
     torch.set_default_dtype(torch.float32)
     from fno.fno3d import SpectralConv3d
     from fno.sfno import SpectralConvS, SpectralConvT
@@ -129,6 +131,24 @@ def sconv_cases():
             out[f"{tag}_g_{key}"] = _np(torch.view_as_real(gp) if gp.is_complex() else gp)
         print(tag, tuple(x.shape), "->", tuple(y.shape))
 
+    if grid32:
+        torch.manual_seed(1)
+        m = SpectralConv3d(3, 2, 6, 5, 4)
+        run("c3d_32", m, torch.randn(2, 3, 32, 32, 10))
+        m = SpectralConvS(2, 3, 8, 16, 3, bias=True, delta=0.5)
+        with torch.no_grad():
+            for b in m.bias:
+                b.copy_(torch.randn_like(b))
+        run("cs_32_bias", m, torch.randn(1, 2, 64, 32, 6))
+        m = SpectralConvS(2, 2, 4, 4, 4, norm="ortho")
+        run("cs_32_outT", m, torch.randn(1, 2, 32, 32, 8), out_mesh_size=[32, 32, 11])
+        m = SpectralConvT(2, 2, 5, 4, 6, out_steps=7, temporal_padding=True, bias=True)
+        with torch.no_grad():
+            for b in m.bias:
+                b.copy_(torch.randn_like(b))
+        run("ct_32_pad", m, torch.randn(2, 2, 32, 32, 5))
+        np.savez_compressed(os.path.join(HERE, "sconv32.npz"), **out)
+        return
     torch.manual_seed(0)
     # SpectralConv3d: (b, C, X, Y, T)
     m = SpectralConv3d(3, 4, 4, 3, 3)
@@ -160,6 +180,9 @@ def sconv_cases():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sconv32":
+        sconv_cases(grid32=True)
+        sys.exit(0)
     # C1 (BASELINE.json configs[0]): 64^2, batch 1, fp64, Kolmogorov vorticity forcing, drag 0.1
     ns2d_case("ns2d_c1_fp64", 64, 1, torch.float64, 1e-3, 0.1, "vorticity", [1, 2, 100], traj=(6, 2))
     # C2-like small: fp32, batch 3, unforced, no drag
@@ -173,3 +196,4 @@ if __name__ == "__main__":
               traj=(4, 1))
     mask_case()
     sconv_cases()
+    sconv_cases(grid32=True)

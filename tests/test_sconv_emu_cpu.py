@@ -1,0 +1,105 @@
+"""CPU tier for hot path B: the spectral-convolution kernels compiled for host threads
+(tests/emu/libtcfd_emu.so, test infrastructure only) against the reference-generated fixtures
+(tests/golden/sconv32.npz) and the oracle, forward AND backward; host-side argument checks."""
+import pytest
+import torch
+
+from _common import ensure_emu_lib, load_golden, rel_l2
+from _sconv_common import GOLDEN32, geometry, golden_params
+from oracle import sconv_oracle as SO
+
+
+def _emu_plan(geom, batch):
+    from torch_cfd_b200 import _lib
+    return _lib.SConv3dPlan(_lib.TcfdLibrary(ensure_emu_lib()), *geom, max_batch=batch)
+
+
+def _run(plan, x, wr, br, delta, cot, T_out):
+    wc = [torch.view_as_complex(w.contiguous()) for w in wr]
+    bc = [torch.view_as_complex(b.contiguous()) for b in br] if br is not None else None
+    b, Co = x.shape[0], wr[0].shape[1]
+    y = torch.empty(b, Co, x.shape[2], x.shape[3], T_out)
+    xhat = torch.empty(plan.xhat_elems(b), dtype=torch.complex64)
+    plan.forward(x.contiguous(), wc, bc, delta, y, xhat)
+    gx = torch.empty_like(x)
+    gw = [torch.empty_like(w) for w in wc]
+    gb = [torch.empty_like(t) for t in bc] if bc is not None else None
+    plan.backward(cot.contiguous(), xhat, wc, gx, gw, gb, delta)
+    return y, gx, [torch.view_as_real(t) for t in gw], None if gb is None else [torch.view_as_real(t) for t in gb]
+
+
+@pytest.mark.parametrize("tag,kind,cfg", GOLDEN32)
+def test_emu_sconv_vs_reference_golden(tag, kind, cfg):
+    g = load_golden("sconv32")
+    x, yref, cot = (torch.from_numpy(g[f"{tag}_{k}"]) for k in ("x", "y", "cot"))
+    wr, br, gwr, gbr = golden_params(g, tag, kind, cfg)
+    geom = geometry(x.shape, yref.shape, cfg)
+    plan = _emu_plan(geom, x.shape[0])
+    y, gx, gw, gb = _run(plan, x, wr, br, cfg.get("delta", 1.0), cot, yref.shape[-1])
+    assert plan.last_launch_count == 6  # backward = planes, x-axis, 2 mix kernels, x-axis, planes
+    tol = 2e-6  # fp32: forward 1e-5 / gradients 1e-4 are the bars of SURVEY 8d; this is what we get
+    assert rel_l2(y, yref) < tol
+    assert rel_l2(gx, torch.from_numpy(g[f"{tag}_gx"])) < tol
+    for a, b in zip(gw, gwr):
+        assert rel_l2(a, b) < tol
+    if gb is not None:
+        for a, b in zip(gb, gbr):
+            assert rel_l2(a, b) < tol
+
+
+@pytest.mark.parametrize("shape,modes,kw", [
+    ((2, 3, 32, 64, 9), (5, 7, 4), dict()),                                      # odd T
+    ((1, 2, 64, 32, 12), (32, 16, 7), dict(bias=True, delta=0.3)),                # mx = X/2, my = Y/2 (full)
+    ((1, 2, 32, 32, 4), (3, 3, 5), dict(t_pad=4, T_out=9, bias=True, norm="forward")),
+])
+def test_emu_sconv_vs_oracle(shape, modes, kw):
+    torch.manual_seed(3)
+    b, Ci, X, Y, T = shape
+    Co, (mx, my, mt) = 2, modes
+    t_pad, T_out, norm = kw.get("t_pad", 0), kw.get("T_out", T), kw.get("norm", "backward")
+    delta = kw.get("delta", 1.0)
+    x = torch.randn(shape, requires_grad=True)
+    wr = [(0.5 / (Ci * Co) * torch.rand(Ci, Co, mx, my, mt, 2)).requires_grad_() for _ in range(4)]
+    br = [(0.1 * torch.randn(mx, my, mt, 2)).requires_grad_() for _ in range(4)] if kw.get("bias") else None
+    if t_pad:
+        yr = SO.spectral_conv_t(x, wr, mx, my, mt, T_out, br, delta, True, norm)
+    else:
+        yr = SO.spectral_conv_s(x, wr, mx, my, mt, br, delta, [X, Y, T_out], norm)
+    cot = torch.randn_like(yr)
+    yr.backward(cot)
+    plan = _emu_plan((X, Y, T, t_pad, T_out, Ci, Co, mx, my, mt, norm), b)
+    y, gx, gw, gb = _run(plan, x.detach(), [w.detach() for w in wr], None if br is None else [t.detach() for t in br],
+                         delta, cot, T_out)
+    assert rel_l2(y, yr) < 2e-6 and rel_l2(gx, x.grad) < 2e-6
+    for a, w in zip(gw, wr):
+        assert rel_l2(a, w.grad) < 2e-6
+    if gb is not None:
+        for a, t in zip(gb, br):
+            assert rel_l2(a, t.grad) < 2e-6
+
+
+def test_sconv_rejects_what_the_reference_rejects():
+    # modes_t = 8 with T = 10 (6 retained frequencies): the reference's einsum raises (SURVEY 8d, C4 note)
+    with pytest.raises(ValueError, match="modes_t"):
+        _emu_plan((32, 32, 10, 0, 10, 2, 2, 4, 4, 8, "backward"), 1)
+    with pytest.raises(ValueError, match="powers of two"):
+        _emu_plan((48, 32, 8, 0, 8, 2, 2, 4, 4, 3, "backward"), 1)
+    with pytest.raises(ValueError, match="overlapping"):
+        _emu_plan((32, 32, 8, 0, 8, 2, 2, 17, 4, 3, "backward"), 1)
+
+
+def test_sconv_modules_mirror_reference_parameters():
+    """Parameter names, shapes, dtypes and init ranges of the shims == the reference modules'."""
+    from torch_cfd_b200.fno import SpectralConv3d, SpectralConvS, SpectralConvT
+    m = SpectralConv3d(3, 4, 5, 6, 3)
+    assert sorted(n for n, _ in m.named_parameters()) == ["weights1", "weights2", "weights3", "weights4"]
+    assert m.weights1.shape == (3, 4, 5, 6, 3) and m.weights1.dtype == torch.cfloat
+    assert float(m.weights1.real.max()) <= 1 / 12 and float(m.weights1.real.min()) >= 0
+    s = SpectralConvS(2, 3, 4, 4, 3, bias=True)
+    assert sorted(n for n, _ in s.named_parameters()) == [f"bias.{i}" for i in range(4)] + [f"weight.{i}" for i in range(4)]
+    assert s.weight[0].shape == (2, 3, 4, 4, 3, 2) and s.bias[0].shape == (4, 4, 3, 2)
+    assert float(s.weight[0].max()) <= 0.5 / 6 and torch.count_nonzero(s.bias[0]) == 0
+    t = SpectralConvT(2, 2, 4, 4, 3, out_steps=5)
+    assert t.delta == 1e-1 and t.bias is not False and t.out_steps == 5
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 32, 32, 8))

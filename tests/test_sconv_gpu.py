@@ -1,0 +1,121 @@
+"""GPU parity tests of hot path B (pytest -m gpu): module shim -> autograd.Function -> ctypes ->
+C ABI -> sm_100a kernels, against the reference-generated fixtures, the oracle (values and torch
+autograd gradients) and, at BASELINE's C4/C5 sizes, adjointness / linearity properties."""
+import pytest
+import torch
+
+from _common import load_golden, rel_l2
+from _sconv_common import GOLDEN32, golden_params
+from oracle import sconv_oracle as SO
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _module(kind, cfg, wr, br):
+    from torch_cfd_b200.fno import SpectralConv3d, SpectralConvS, SpectralConvT
+    mx, my, mt = cfg["modes"]
+    if kind == "c3d":
+        m = SpectralConv3d(cfg["Ci"], cfg["Co"], mx, my, mt)
+        with torch.no_grad():
+            for i, w in enumerate(wr, 1):
+                getattr(m, f"weights{i}").copy_(torch.view_as_complex(w))
+        return m.to(DEV)
+    if kind == "cs":
+        m = SpectralConvS(cfg["Ci"], cfg["Co"], mx, my, mt, bias=bool(cfg.get("bias")), delta=cfg.get("delta", 1),
+                          norm=cfg.get("norm", "backward"))
+    else:
+        m = SpectralConvT(cfg["Ci"], cfg["Co"], mx, my, mt, delta=cfg.get("delta", 0.1), out_steps=cfg.get("out_steps"),
+                          bias=bool(cfg.get("bias")), temporal_padding=bool(cfg.get("temporal_padding")),
+                          norm=cfg.get("norm", "backward"))
+    with torch.no_grad():
+        for p, w in zip(m.weight, wr):
+            p.copy_(w)
+        if br is not None:
+            for p, b in zip(m.bias, br):
+                p.copy_(b)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("tag,kind,cfg", GOLDEN32)
+def test_modules_vs_reference_golden(tag, kind, cfg):
+    g = load_golden("sconv32")
+    x = torch.from_numpy(g[f"{tag}_x"]).to(DEV).requires_grad_(True)
+    yref, cot = torch.from_numpy(g[f"{tag}_y"]), torch.from_numpy(g[f"{tag}_cot"])
+    wr, br, gwr, gbr = golden_params(g, tag, kind, cfg)
+    m = _module(kind, cfg, wr, br)
+    y = m(x, out_mesh_size=cfg["out_mesh"]) if "out_mesh" in cfg else m(x)
+    assert y.shape == yref.shape and y.is_cuda and y.dtype == torch.float32
+    (y * cot.to(DEV)).sum().backward()
+    tol = 2e-6
+    assert rel_l2(y, yref) < tol
+    assert rel_l2(x.grad, torch.from_numpy(g[f"{tag}_gx"])) < tol
+    params = [getattr(m, f"weights{i}") for i in range(1, 5)] if kind == "c3d" else list(m.weight)
+    for p, ref in zip(params, gwr):
+        got = torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad
+        assert rel_l2(got, ref) < tol
+    if gbr is not None:
+        for p, ref in zip(m.bias, gbr):
+            assert rel_l2(p.grad, ref) < tol
+
+
+@pytest.mark.parametrize("X,Y,T,modes", [(64, 128, 10, (12, 20, 6)), (256, 64, 16, (20, 8, 8)), (128, 128, 7, (8, 8, 4))])
+def test_modules_vs_oracle_sizes(X, Y, T, modes):
+    from torch_cfd_b200.fno import SpectralConvS
+    torch.manual_seed(5)
+    mx, my, mt = modes
+    m = SpectralConvS(3, 2, mx, my, mt, bias=True, delta=0.7)
+    with torch.no_grad():
+        for b in m.bias:
+            b.copy_(0.2 * torch.randn_like(b))
+    x = torch.randn(2, 3, X, Y, T)
+    xr = x.clone().requires_grad_(True)
+    wr = [w.detach().clone().requires_grad_() for w in m.weight]
+    br = [b.detach().clone().requires_grad_() for b in m.bias]
+    yr = SO.spectral_conv_s(xr, wr, mx, my, mt, br, 0.7)
+    cot = torch.randn_like(yr)
+    yr.backward(cot)
+    m = m.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    y = m(xg)
+    y.backward(cot.to(DEV))
+    assert rel_l2(y, yr) < 1e-5          # forward 1e-5 relative
+    assert rel_l2(xg.grad, xr.grad) < 1e-4  # gradients 1e-4 relative
+    for p, w in zip(m.weight, wr):
+        assert rel_l2(p.grad, w.grad) < 1e-4
+    for p, b in zip(m.bias, br):
+        assert rel_l2(p.grad, b.grad) < 1e-4
+
+
+def test_c4_size_properties():
+    """C4's geometry (b reduced to 4): SpectralConvT with temporal padding, 256^2, T=10, modes (20,20,8),
+    width 20.  Adjointness <y, A x'> == <A^T y, x'> of forward/backward, linearity in x, and an oracle
+    check of one sample."""
+    from torch_cfd_b200.fno import SpectralConvT
+    torch.manual_seed(7)
+    m = SpectralConvT(20, 20, 20, 20, 8, out_steps=10, temporal_padding=True, bias=False).to(DEV)
+    x1 = torch.randn(4, 20, 256, 256, 10, device=DEV, requires_grad=True)
+    x2 = torch.randn(4, 20, 256, 256, 10, device=DEV)
+    y1 = m(x1)
+    cot = torch.randn_like(y1)
+    (gx,) = torch.autograd.grad(y1, x1, cot)
+    with torch.no_grad():
+        y2 = m(x2)
+        lhs = (cot * y2).double().sum().item()
+        rhs = (gx * x2).double().sum().item()
+        assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), 1.0)
+        y12 = m(x1.detach() + 2 * x2)
+        assert rel_l2(y12, y1.detach() + 2 * y2) < 1e-5
+        yr = SO.spectral_conv_t(x2[:1].cpu(), [w.detach().cpu() for w in m.weight], 20, 20, 8, 10, None, 0.1, True)
+        assert rel_l2(y2[:1], yr) < 1e-5
+
+
+def test_errors_on_gpu():
+    from torch_cfd_b200.fno import SpectralConv3d
+    m = SpectralConv3d(2, 2, 4, 4, 8).to(DEV)
+    with pytest.raises(ValueError, match="modes_t"):
+        m(torch.zeros(1, 2, 32, 32, 10, device=DEV))  # T/2+1 = 6 < 8: the reference raises as well
+    with pytest.raises(TypeError):
+        m(torch.zeros(1, 2, 32, 32, 16, device=DEV, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 32, 32, 16, device=DEV))

@@ -31,6 +31,11 @@ class _Desc(ctypes.Structure):
     ]
 
 
+class _SconvDesc(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int) for k in
+                ("X", "Y", "T_in", "t_pad", "T_out", "Ci", "Co", "mx", "my", "mt", "norm", "max_batch")]
+
+
 class TcfdLibrary:
     """A loaded libtcfd with typed entry points."""
 
@@ -59,6 +64,16 @@ class TcfdLibrary:
                                            ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
         c.tcfd_ns2d_explicit_terms.argtypes = [vp, vp, vp, ci, vp]
         c.tcfd_ns2d_residual.argtypes = [vp, vp, vp, vp, ci, vp]
+        pp = ctypes.POINTER(vp)
+        c.tcfd_sconv3d_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_SconvDesc)]
+        c.tcfd_sconv3d_destroy.argtypes = [vp]
+        c.tcfd_sconv3d_workspace_bytes.argtypes = [vp]
+        c.tcfd_sconv3d_workspace_bytes.restype = ctypes.c_size_t
+        c.tcfd_sconv3d_xhat_elems.argtypes = [vp, ci]
+        c.tcfd_sconv3d_xhat_elems.restype = ctypes.c_size_t
+        c.tcfd_sconv3d_last_launch_count.argtypes = [vp]
+        c.tcfd_sconv3d_forward.argtypes = [vp, vp, pp, pp, ctypes.c_float, vp, vp, ci, vp]
+        c.tcfd_sconv3d_backward.argtypes = [vp, vp, vp, pp, vp, pp, pp, ctypes.c_float, ci, vp]
 
     def check(self, rc: int, what: str):
         if rc != 0:
@@ -195,3 +210,58 @@ class NS2DPlan:
         self.lib.check(self.lib.c.tcfd_ns2d_residual(self._h, w_in.data_ptr(), wt_in.data_ptr(), out.data_ptr(),
                                                      w_in.shape[0], _stream_handle(w_in)),
                        "tcfd_ns2d_residual")
+
+
+_NORMS = {"backward": 0, None: 0, "ortho": 1, "forward": 2}
+
+
+def _ptr_array(tensors):
+    if tensors is None:
+        return None
+    return (ctypes.c_void_p * 4)(*[t.data_ptr() for t in tensors])
+
+
+class SConv3dPlan:
+    """Owns one ``tcfd_sconv3d_t`` handle (t-axis tables, twiddles, spectral workspace) for one
+    layer geometry on the current device."""
+
+    def __init__(self, lib: TcfdLibrary, X, Y, T_in, t_pad, T_out, Ci, Co, mx, my, mt, norm, max_batch):
+        self.lib = lib
+        self.geom = (X, Y, T_in, t_pad, T_out, Ci, Co, mx, my, mt, norm)
+        self.max_batch = max_batch
+        self._h = ctypes.c_void_p()
+        d = _SconvDesc(X, Y, T_in, t_pad, T_out, Ci, Co, mx, my, mt, _NORMS[norm], max_batch)
+        rc = lib.c.tcfd_sconv3d_create(ctypes.byref(self._h), ctypes.byref(d))
+        if rc != 0:
+            msg = lib.c.tcfd_last_error().decode("utf-8", "replace")
+            raise ValueError(f"torch-cfd_b200: tcfd_sconv3d_create failed ({rc}): {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.c.tcfd_sconv3d_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.c.tcfd_sconv3d_last_launch_count(self._h))
+
+    def xhat_elems(self, batch: int) -> int:
+        return int(self.lib.c.tcfd_sconv3d_xhat_elems(self._h, batch))
+
+    def forward(self, x, w, bias, delta, y, xhat):
+        rc = self.lib.c.tcfd_sconv3d_forward(self._h, x.data_ptr(), _ptr_array(w), _ptr_array(bias), float(delta),
+                                             y.data_ptr(), None if xhat is None else xhat.data_ptr(),
+                                             x.shape[0], _stream_handle(x))
+        self.lib.check(rc, "tcfd_sconv3d_forward")
+
+    def backward(self, gy, xhat, w, gx, gw, gbias, delta):
+        rc = self.lib.c.tcfd_sconv3d_backward(self._h, gy.data_ptr(), xhat.data_ptr(), _ptr_array(w),
+                                              None if gx is None else gx.data_ptr(), _ptr_array(gw),
+                                              _ptr_array(gbias), float(delta), gy.shape[0], _stream_handle(gy))
+        self.lib.check(rc, "tcfd_sconv3d_backward")

@@ -65,6 +65,8 @@ struct tcfd_ns2d {
 };
 
 extern "C" const char* tcfd_last_error(void) { return g_err.c_str(); }
+// internal: lets the other translation units of the library report through tcfd_last_error()
+extern "C" void tcfd_set_last_error(const char* msg) { g_err = msg ? msg : ""; }
 extern "C" const char* tcfd_version(void) {
 #ifdef TCFD_EMU
   return "tcfd 0.1 host-emulation (tests only)";

@@ -1,0 +1,307 @@
+// C ABI of hot path B (see include/tcfd.h): host driver of the pruned spectral convolution.
+// Owns the t-axis tables, the FFT twiddles and the (small) spectral workspaces; the arithmetic
+// lives in sconv_kernels.cuh.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tcfd.h"
+#include "sconv_kernels.cuh"
+
+extern "C" void tcfd_set_last_error(const char* msg);
+
+namespace {
+thread_local std::string g_serr;
+int sfail(int code, const std::string& msg) {
+  g_serr = msg;
+  tcfd_set_last_error(msg.c_str());
+  return code;
+}
+#define SCUDA_TRY(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return sfail(TCFD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+
+typedef tcfd::cx<float> cplx;
+const double PI = 3.14159265358979323846264338327950288;
+
+template <class K>
+int set_smem(K kernel, size_t smem) {
+#ifndef TCFD_EMU
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+#else
+  (void)kernel;
+  (void)smem;
+#endif
+  return 0;
+}
+}  // namespace
+
+struct tcfd_sconv3d {
+  tcfd_sconv3d_desc_t d{};
+  int Tn_in = 0, Tn_out = 0, K = 0;
+  void *twx = nullptr, *twy = nullptr;
+  void *A_f = nullptr, *S_f = nullptr, *A_b = nullptr, *S_b = nullptr;
+  void *Z = nullptr, *H1 = nullptr, *H2 = nullptr;
+  size_t ws_bytes = 0;
+  int launches = 0;
+};
+
+namespace {
+int upload_c(void** dst, const std::vector<cplx>& v) {
+  SCUDA_TRY(cudaMalloc(dst, v.size() * sizeof(cplx)));
+  SCUDA_TRY(cudaMemcpy(*dst, v.data(), v.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+  return 0;
+}
+std::vector<cplx> twiddles(int n) {
+  std::vector<cplx> tw(n);
+  for (int j = 0; j < n; ++j) {
+    const double a = -2.0 * PI * (double)j / (double)n;
+    tw[j] = cplx{(float)std::cos(a), (float)std::sin(a)};
+  }
+  return tw;
+}
+bool pow2_ok(int n) { return n >= 32 && n <= 512 && (n & (n - 1)) == 0; }
+
+using namespace tcfd;
+
+template <int Y>
+int launch_planes_fwd(const float* x, cplx* Z1, const cplx* A, const cplx* tw, SconvDims d, int nplanes, cudaStream_t st) {
+  typedef PlanesSmem<Y> S;
+  const size_t smem = S::GP * S::group_bytes(d.Tin, d.my);
+  if (smem > 227 * 1024) return -100;
+  auto k = sconv_planes_fwd_kernel<Y>;
+  if (int rc = set_smem(k, smem)) return rc;
+  TCFD_LAUNCH(k, (nplanes + S::GP - 1) / S::GP, S::GP * S::NT, smem, st, x, Z1, A, tw, d, nplanes);
+  return 0;
+}
+template <int Y>
+int launch_planes_inv(const cplx* Z2, float* y, const cplx* Sy, const cplx* tw, SconvDims d, int nplanes, cudaStream_t st) {
+  typedef PlanesSmem<Y> S;
+  const size_t smem = S::GP * S::group_bytes(d.Tout, d.my);
+  if (smem > 227 * 1024) return -100;
+  auto k = sconv_planes_inv_kernel<Y>;
+  if (int rc = set_smem(k, smem)) return rc;
+  TCFD_LAUNCH(k, (nplanes + S::GP - 1) / S::GP, S::GP * S::NT, smem, st, Z2, y, Sy, tw, d, nplanes);
+  return 0;
+}
+template <int X, bool FWD>
+int launch_xaxis(const cplx* in, cplx* out, const cplx* tw, SconvDims d, int ncol, int nslabs, cudaStream_t st) {
+  typedef XaxisSmem<X> S;
+  auto k = sconv_xaxis_kernel<X, FWD>;
+  if (int rc = set_smem(k, S::BYTES)) return rc;
+  const int npairs = (ncol + 1) / 2;
+  TCFD_LAUNCH3(k, (npairs + S::GP - 1) / S::GP, nslabs, 1, S::GP * S::NT, S::BYTES, st, in, out, tw, d, ncol);
+  return 0;
+}
+
+#define SCONV_SIZES(F) F(32) F(64) F(128) F(256) F(512)
+
+int planes_fwd(int Y, const float* x, cplx* Z1, const cplx* A, const cplx* tw, SconvDims d, int np, cudaStream_t st) {
+#define CASE(n) if (Y == n) return launch_planes_fwd<n>(x, Z1, A, tw, d, np, st);
+  SCONV_SIZES(CASE)
+#undef CASE
+  return -1;
+}
+int planes_inv(int Y, const cplx* Z2, float* y, const cplx* Sy, const cplx* tw, SconvDims d, int np, cudaStream_t st) {
+#define CASE(n) if (Y == n) return launch_planes_inv<n>(Z2, y, Sy, tw, d, np, st);
+  SCONV_SIZES(CASE)
+#undef CASE
+  return -1;
+}
+int xaxis(int X, bool fwd, const cplx* in, cplx* out, const cplx* tw, SconvDims d, int ncol, int nslabs, cudaStream_t st) {
+#define CASE(n)                                                                       \
+  if (X == n) return fwd ? launch_xaxis<n, true>(in, out, tw, d, ncol, nslabs, st)    \
+                         : launch_xaxis<n, false>(in, out, tw, d, ncol, nslabs, st);
+  SCONV_SIZES(CASE)
+#undef CASE
+  return -1;
+}
+
+int check_launch(tcfd_sconv3d* h, int rc, const char* what) {
+  h->launches++;
+  if (rc == -100) return sfail(TCFD_ERR_INVALID, std::string(what) + ": shared-memory footprint exceeds 227 KB (T too large)");
+  if (rc != 0) return sfail(TCFD_ERR_CUDA, std::string(what) + ": launch failed (" + std::to_string(rc) + ")");
+#ifndef TCFD_EMU
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return sfail(TCFD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+#endif
+  return 0;
+}
+
+SconvDims dims_of(const tcfd_sconv3d* h, int Tin, int Tout, int nslabs) {
+  SconvDims d;
+  d.X = h->d.X; d.Y = h->d.Y; d.mx = h->d.mx; d.my = h->d.my; d.mt = h->d.mt;
+  d.Tin = Tin; d.Tout = Tout; d.nplanes_c = nslabs;
+  return d;
+}
+}  // namespace
+
+extern "C" int tcfd_sconv3d_create(tcfd_sconv3d_t** out, const tcfd_sconv3d_desc_t* d) {
+  if (!out || !d) return sfail(TCFD_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (!pow2_ok(d->X) || !pow2_ok(d->Y)) return sfail(TCFD_ERR_INVALID, "X and Y must be powers of two in [32, 512]");
+  if (d->T_in < 1 || d->T_out < 1 || d->t_pad < 0) return sfail(TCFD_ERR_INVALID, "bad T_in / T_out / t_pad");
+  if (d->Ci < 1 || d->Co < 1 || d->max_batch < 1) return sfail(TCFD_ERR_INVALID, "bad channel count or batch");
+  const int Tn_in = d->T_in + d->t_pad, Tn_out = d->T_out + d->t_pad;
+  if (d->mx < 1 || d->my < 1 || d->mt < 1 || 2 * d->mx > d->X || 2 * d->my > d->Y)
+    return sfail(TCFD_ERR_INVALID, "modes must satisfy 1 <= mx <= X/2, 1 <= my <= Y/2 (overlapping corner blocks are not supported)");
+  if (d->mt > Tn_in / 2 + 1)
+    return sfail(TCFD_ERR_INVALID, "modes_t exceeds the " + std::to_string(Tn_in / 2 + 1) +
+                                       " retained t-frequencies of the input (the reference's einsum raises here too)");
+  if (d->norm < 0 || d->norm > 2) return sfail(TCFD_ERR_INVALID, "norm must be 0 (backward), 1 (ortho) or 2 (forward)");
+  tcfd_sconv3d* h = new tcfd_sconv3d();
+  h->d = *d;
+  h->Tn_in = Tn_in;
+  h->Tn_out = Tn_out;
+  h->K = 4 * d->mx * d->my * d->mt;
+  const double n_in = (double)d->X * d->Y * Tn_in, n_out = (double)d->X * d->Y * Tn_out;
+  const double fs = d->norm == 0 ? 1.0 : (d->norm == 1 ? 1.0 / std::sqrt(n_in) : 1.0 / n_in);
+  const double is = d->norm == 0 ? 1.0 / n_out : (d->norm == 1 ? 1.0 / std::sqrt(n_out) : 1.0);
+  const int mt = d->mt;
+  std::vector<cplx> A_f((size_t)mt * d->T_in), S_f((size_t)d->T_out * mt), A_b((size_t)mt * d->T_out), S_b((size_t)d->T_in * mt);
+  for (int kt = 0; kt < mt; ++kt)
+    for (int t = 0; t < d->T_in; ++t) {
+      const double th = -2.0 * PI * (double)((long long)kt * (t + d->t_pad) % Tn_in) / (double)Tn_in;
+      A_f[(size_t)kt * d->T_in + t] = cplx{(float)(fs * std::cos(th)), (float)(fs * std::sin(th))};
+      S_b[(size_t)t * mt + kt] = cplx{(float)(fs * std::cos(th)), (float)(-fs * std::sin(th))};
+    }
+  for (int t = 0; t < d->T_out; ++t)
+    for (int kt = 0; kt < mt; ++kt) {
+      double s = 2.0;
+      if (kt == 0 || (Tn_out % 2 == 0 && kt == Tn_out / 2)) s = 1.0;
+      if (kt > Tn_out / 2) s = 0.0;  // beyond the output's Nyquist: dropped by irfftn(s=...)
+      const double th = 2.0 * PI * (double)((long long)kt * (t + d->t_pad) % Tn_out) / (double)Tn_out;
+      const double re = is * s * std::cos(th), im = is * s * std::sin(th);
+      S_f[(size_t)t * mt + kt] = cplx{(float)re, (float)im};
+      A_b[(size_t)kt * d->T_out + t] = cplx{(float)re, (float)(-im)};
+    }
+  int rc = 0;
+  if (!rc) rc = upload_c(&h->twx, twiddles(d->X));
+  if (!rc) rc = upload_c(&h->twy, twiddles(d->Y));
+  if (!rc) rc = upload_c(&h->A_f, A_f);
+  if (!rc) rc = upload_c(&h->S_f, S_f);
+  if (!rc) rc = upload_c(&h->A_b, A_b);
+  if (!rc) rc = upload_c(&h->S_b, S_b);
+  const int cmax = d->Ci > d->Co ? d->Ci : d->Co;
+  const size_t zb = (size_t)d->max_batch * cmax * d->X * 2 * d->my * mt * sizeof(cplx);
+  const size_t hb = (size_t)d->max_batch * cmax * h->K * sizeof(cplx);
+  if (!rc && cudaMalloc(&h->Z, zb) != cudaSuccess) rc = sfail(TCFD_ERR_NOMEM, "workspace allocation failed");
+  if (!rc && cudaMalloc(&h->H1, hb) != cudaSuccess) rc = sfail(TCFD_ERR_NOMEM, "workspace allocation failed");
+  if (!rc && cudaMalloc(&h->H2, hb) != cudaSuccess) rc = sfail(TCFD_ERR_NOMEM, "workspace allocation failed");
+  h->ws_bytes = zb + 2 * hb;
+  if (rc) {
+    std::string keep = g_serr;
+    tcfd_sconv3d_destroy(h);
+    tcfd_set_last_error(keep.c_str());
+    return rc;
+  }
+  *out = h;
+  return TCFD_OK;
+}
+
+extern "C" int tcfd_sconv3d_destroy(tcfd_sconv3d_t* h) {
+  if (!h) return TCFD_OK;
+  void* all[] = {h->twx, h->twy, h->A_f, h->S_f, h->A_b, h->S_b, h->Z, h->H1, h->H2};
+  for (void* p : all)
+    if (p) cudaFree(p);
+  delete h;
+  return TCFD_OK;
+}
+
+extern "C" size_t tcfd_sconv3d_workspace_bytes(const tcfd_sconv3d_t* h) { return h ? h->ws_bytes : 0; }
+extern "C" size_t tcfd_sconv3d_xhat_elems(const tcfd_sconv3d_t* h, int batch) {
+  return h ? (size_t)batch * h->d.Ci * h->K : 0;
+}
+extern "C" int tcfd_sconv3d_last_launch_count(const tcfd_sconv3d_t* h) { return h ? h->launches : 0; }
+
+extern "C" int tcfd_sconv3d_forward(tcfd_sconv3d_t* h, const void* x, const void* const* w, const void* const* bias,
+                                    float delta, void* y, void* xhat_save, int batch, void* stream_) {
+  if (!h || !x || !w || !y) return sfail(TCFD_ERR_INVALID, "null argument");
+  if (batch < 1 || batch > h->d.max_batch) return sfail(TCFD_ERR_INVALID, "batch outside [1, max_batch]");
+  for (int c = 0; c < 4; ++c)
+    if (!w[c]) return sfail(TCFD_ERR_INVALID, "null weight pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const tcfd_sconv3d_desc_t& d = h->d;
+  const int ncol = 2 * d.my * d.mt;
+  h->launches = 0;
+  cplx* Xh = xhat_save ? static_cast<cplx*>(xhat_save) : static_cast<cplx*>(h->H1);
+  cplx* Yh = static_cast<cplx*>(h->H2);
+  cplx* Z = static_cast<cplx*>(h->Z);
+  int rc;
+  SconvDims dm = dims_of(h, d.T_in, d.T_out, batch * d.Ci);
+  rc = check_launch(h, planes_fwd(d.Y, static_cast<const float*>(x), Z, static_cast<const cplx*>(h->A_f),
+                                  static_cast<const cplx*>(h->twy), dm, batch * d.Ci * d.X, st), "planes_fwd");
+  if (rc) return rc;
+  rc = check_launch(h, xaxis(d.X, true, Z, Xh, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Ci, st), "xaxis_fwd");
+  if (rc) return rc;
+  MixArgs a{};
+  for (int c = 0; c < 4; ++c) {
+    a.w[c] = static_cast<const cplx*>(w[c]);
+    a.bias[c] = bias ? static_cast<const cplx*>(bias[c]) : nullptr;
+  }
+  a.B = batch; a.Ci = d.Ci; a.Co = d.Co; a.delta = delta;
+  TCFD_LAUNCH3(sconv_mix_fwd_kernel, (h->K + 127) / 128, d.Co, 1, 128, 0, st, Xh, Yh, a, dm);
+  if ((rc = check_launch(h, 0, "mix_fwd"))) return rc;
+  dm = dims_of(h, d.T_in, d.T_out, batch * d.Co);
+  rc = check_launch(h, xaxis(d.X, false, Yh, Z, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Co, st), "xaxis_inv");
+  if (rc) return rc;
+  rc = check_launch(h, planes_inv(d.Y, Z, static_cast<float*>(y), static_cast<const cplx*>(h->S_f),
+                                  static_cast<const cplx*>(h->twy), dm, batch * d.Co * d.X, st), "planes_inv");
+  return rc;
+}
+
+extern "C" int tcfd_sconv3d_backward(tcfd_sconv3d_t* h, const void* grad_y, const void* xhat, const void* const* w,
+                                     void* grad_x, void* const* grad_w, void* const* grad_bias, float delta, int batch,
+                                     void* stream_) {
+  if (!h || !grad_y || !xhat || !w) return sfail(TCFD_ERR_INVALID, "null argument");
+  if (batch < 1 || batch > h->d.max_batch) return sfail(TCFD_ERR_INVALID, "batch outside [1, max_batch]");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const tcfd_sconv3d_desc_t& d = h->d;
+  const int ncol = 2 * d.my * d.mt;
+  h->launches = 0;
+  cplx* gYh = static_cast<cplx*>(h->H1);
+  cplx* gXh = static_cast<cplx*>(h->H2);
+  cplx* Z = static_cast<cplx*>(h->Z);
+  int rc;
+  // adjoint of the inverse half: analysis of grad_y with the conjugate-transposed synthesis table
+  SconvDims dm = dims_of(h, d.T_out, d.T_in, batch * d.Co);
+  rc = check_launch(h, planes_fwd(d.Y, static_cast<const float*>(grad_y), Z, static_cast<const cplx*>(h->A_b),
+                                  static_cast<const cplx*>(h->twy), dm, batch * d.Co * d.X, st), "planes_fwd(bwd)");
+  if (rc) return rc;
+  rc = check_launch(h, xaxis(d.X, true, Z, gYh, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Co, st), "xaxis_fwd(bwd)");
+  if (rc) return rc;
+  MixArgs a{};
+  for (int c = 0; c < 4; ++c) {
+    if (!w[c]) return sfail(TCFD_ERR_INVALID, "null weight pointer");
+    a.w[c] = static_cast<const cplx*>(w[c]);
+    a.gw[c] = grad_w ? static_cast<cplx*>(grad_w[c]) : nullptr;
+    a.gbias[c] = grad_bias ? static_cast<cplx*>(grad_bias[c]) : nullptr;
+  }
+  a.B = batch; a.Ci = d.Ci; a.Co = d.Co; a.delta = delta;
+  if (grad_w) {
+    for (int c = 0; c < 4; ++c)
+      if (!grad_w[c]) return sfail(TCFD_ERR_INVALID, "null grad_w pointer");
+    TCFD_LAUNCH3(sconv_mix_bwd_w_kernel, (h->K + 127) / 128, d.Co, d.Ci, 128, 0, st, static_cast<const cplx*>(xhat), gYh, a, dm);
+    if ((rc = check_launch(h, 0, "mix_bwd_w"))) return rc;
+  }
+  if (grad_x) {
+    TCFD_LAUNCH3(sconv_mix_bwd_x_kernel, (h->K + 127) / 128, d.Ci, 1, 128, 0, st, gYh, gXh, a, dm);
+    if ((rc = check_launch(h, 0, "mix_bwd_x"))) return rc;
+    dm = dims_of(h, d.T_out, d.T_in, batch * d.Ci);
+    rc = check_launch(h, xaxis(d.X, false, gXh, Z, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Ci, st), "xaxis_inv(bwd)");
+    if (rc) return rc;
+    rc = check_launch(h, planes_inv(d.Y, Z, static_cast<float*>(grad_x), static_cast<const cplx*>(h->S_b),
+                                    static_cast<const cplx*>(h->twy), dm, batch * d.Ci * d.X, st), "planes_inv(bwd)");
+    if (rc) return rc;
+  }
+  return TCFD_OK;
+}

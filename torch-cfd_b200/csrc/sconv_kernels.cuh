@@ -1,0 +1,413 @@
+// Kernels of hot path B: the FNO3d / SFNO spectral convolution  y = irfftn( W (.) rfftn(x) )  on the
+// four retained corner blocks (reference: fno/fno3d.py:86-116, fno/sfno.py:364-391, :433-457,
+// fno/base.py:229-237).  fp32, x = (b, C, X, Y, T) with T innermost (the real-to-complex axis).
+//
+// Only 2mx * 2my * mt modes survive, so the transforms are PRUNED and the full spectrum is never
+// materialised:
+//   planes_fwd   per (b, c, x) plane [Y][T]: y-axis FFT of the real rows, two time samples per
+//                complex transform and two transforms per thread (packed f32x2 lanes), kept ky only,
+//                then the t-axis analysis as a small dense table product  ->  Z1 (b c, X, 2my, mt)
+//   xaxis<FWD>   x-axis FFT of Z1 columns (two columns per packed transform), kept kx only
+//                                                                   ->  Xh (b c, 2mx, 2my, mt)
+//   mix_fwd      per mode  Yh[b,o] = sum_i Xh[b,i] W[i,o] (+ delta bias)   (complex, CUDA cores:
+//                ~1 GFLOP against 3.4 GB of activations)
+//   xaxis<INV>   zero-padded x-axis inverse                          ->  Z2 (b c, X, 2my, mt)
+//   planes_inv   per plane: t-axis synthesis on the kept ky (table product), Hermitian part, y-axis
+//                inverse FFT with two real outputs per complex transform  ->  y (b, C, X, Y, T')
+// The t axis is table driven (any T, front zero padding, output resampling, normalisation and the
+// C2R doubling all live in the host-built tables), which also makes the BACKWARD pass the same five
+// kernels with conjugate-transposed tables (see sconv_api.cu).
+#pragma once
+#include "fft_core.cuh"
+
+namespace tcfd {
+
+struct CtaSyncS {
+  TCFD_D void operator()() const { __syncthreads(); }
+};
+
+struct SconvDims {
+  int X, Y;            // spatial grid (powers of two)
+  int mx, my, mt;      // retained modes; NKX = 2 mx, NKY = 2 my
+  int Tin, Tout;       // time samples read / written by the plane kernels
+  int nplanes_c;       // number of (b, c) slabs
+};
+
+TCFD_HD int kept_index(int k, int n, int m) {  // index of frequency k in the kept set, or -1
+  if (k < m) return k;
+  if (k >= n - m) return k - (n - 2 * m);
+  return -1;
+}
+TCFD_HD int kept_freq(int ki, int n, int m) { return ki < m ? ki : n - 2 * m + ki; }
+
+// ------------------------------------------------------------------------------------------
+// planes_fwd.  CTA = GP groups of NT = Y/8 threads; group g works on plane blockIdx.x*GP + g.
+// A(kt, t): analysis table [mt][Tin] complex.
+// shared memory per group: tile [Y*Tin] floats | exchange Y cx<f2> | E (2my+1) cx<f2> | Xy [2my][Tq*4] cx<float>
+template <int Y>
+struct PlanesSmem {
+  static constexpr int NT = Y / 8;
+  static constexpr int GP = (128 / NT) > 0 ? (128 / NT) : 1;
+  TCFD_HD static int tq(int T) { return (T + 3) / 4; }
+  TCFD_HD static size_t group_bytes(int T, int my) {
+    size_t b = (size_t)Y * T * 4;                         // plane tile
+    b = (b + 15) / 16 * 16 + (size_t)Y * 16;              // exchange
+    b += (size_t)(2 * my + 1) * 16;                       // E / Dh entries
+    b += (size_t)(2 * my) * tq(T) * 4 * 8;                // Xy / D
+    return (b + 15) / 16 * 16;
+  }
+};
+
+template <int Y>
+__global__ void __launch_bounds__(PlanesSmem<Y>::GP * (Y / 8))
+sconv_planes_fwd_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1, const cx<float>* __restrict__ A,
+                        const cx<float>* __restrict__ twtab, SconvDims d, int nplanes) {
+  typedef PlanesSmem<Y> S;
+  constexpr int NT = S::NT, GP = S::GP;
+  const int T = d.Tin, my = d.my, mt = d.mt, NKY = 2 * my, TQ = S::tq(T);
+  TCFD_DYN_SMEM(smem_raw);
+  const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+  unsigned char* base = smem_raw + (size_t)g * S::group_bytes(T, my);
+  float* tile = reinterpret_cast<float*>(base);
+  cx<f2>* buf = reinterpret_cast<cx<f2>*>(base + ((size_t)Y * T * 4 + 15) / 16 * 16);
+  cx<f2>* Es = buf + Y;
+  cx<float>* Xy = reinterpret_cast<cx<float>*>(Es + (2 * my + 1));  // [NKY][TQ*4]
+  FftTwiddles<float, Y> tw;
+  tw.load(twtab, t);
+  CtaSyncS sync;
+  int parity = 0;
+  const int plane = blockIdx.x * GP + g;
+  const bool valid = plane < nplanes;
+  const int pl = valid ? plane : nplanes - 1;
+
+  // stage the plane (contiguous Y*T floats)
+  const float* src = x + (size_t)pl * Y * T;
+  for (int i = t; i < Y * T; i += NT) tile[i] = src[i];
+  __syncthreads();
+  for (int q = 0; q < TQ; ++q) {
+    cx<f2> z[1][8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const float* r = tile + (t + m * NT) * T + 4 * q;
+      const float v0 = r[0], v1 = (4 * q + 1 < T) ? r[1] : 0.f, v2 = (4 * q + 2 < T) ? r[2] : 0.f,
+                  v3 = (4 * q + 3 < T) ? r[3] : 0.f;
+      z[0][m] = cx<f2>{f2(v0, v2), f2(v1, v3)};  // lane lo: x[t0] + i x[t0+1]; lane hi: x[t0+2] + i x[t0+3]
+    }
+    fft_run<f2, Y, -1, 1, false, Y>(z, tw, buf, parity, t, sync);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int ky = t + m * NT;
+      if (ky <= my) Es[ky] = z[0][m];
+      else if (ky >= Y - my) Es[my + 1 + ky - (Y - my)] = z[0][m];
+    }
+    __syncthreads();
+    // separate the two real transforms of each lane at the kept ky
+    for (int kyi = t; kyi < NKY; kyi += NT) {
+      const int ky = kept_freq(kyi, Y, my), kn = (Y - ky) % Y;
+      const cx<f2> e = Es[ky <= my ? ky : my + 1 + ky - (Y - my)];
+      const cx<f2> n = Es[kn <= my ? kn : my + 1 + kn - (Y - my)];
+      // X_a = (E(k) + conj E(-k)) / 2 ;  X_b = (E(k) - conj E(-k)) / (2i)
+      const f2 ar = 0.5f * (e.x + n.x), ai = 0.5f * (e.y - n.y);
+      const f2 br = 0.5f * (e.y + n.y), bi = 0.5f * (n.x - e.x);
+      cx<float>* o = Xy + (size_t)kyi * TQ * 4 + 4 * q;
+      o[0] = cx<float>{ar.lo, ai.lo};
+      o[1] = cx<float>{br.lo, bi.lo};
+      o[2] = cx<float>{ar.hi, ai.hi};
+      o[3] = cx<float>{br.hi, bi.hi};
+    }
+    __syncthreads();
+  }
+  // t-axis analysis on the kept ky:  Z1[kyi][kt] = sum_t A[kt][t] Xy[kyi][t]
+  if (valid) {
+    cx<float>* dst = Z1 + (size_t)plane * NKY * mt;
+    for (int j = t; j < NKY * mt; j += NT) {
+      const int kyi = j / mt, kt = j % mt;
+      const cx<float>* xr = Xy + (size_t)kyi * TQ * 4;
+      const cx<float>* ar = A + (size_t)kt * T;
+      float sr = 0.f, si = 0.f;
+      for (int tt = 0; tt < T; ++tt) {
+        const cx<float> a = ar[tt], v = xr[tt];
+        sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
+        si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
+      }
+      dst[j] = cx<float>{sr, si};
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// planes_inv.  Sy(t, kt): synthesis table [Tout][mt] complex;  y[t] = Re( sum_kt Sy[t][kt] c[kt] ).
+template <int Y>
+__global__ void __launch_bounds__(PlanesSmem<Y>::GP * (Y / 8))
+sconv_planes_inv_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y, const cx<float>* __restrict__ Sy,
+                        const cx<float>* __restrict__ twtab, SconvDims d, int nplanes) {
+  typedef PlanesSmem<Y> S;
+  constexpr int NT = S::NT, GP = S::GP;
+  const int T = d.Tout, my = d.my, mt = d.mt, NKY = 2 * my, TQ = S::tq(T);
+  TCFD_DYN_SMEM(smem_raw);
+  const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+  unsigned char* base = smem_raw + (size_t)g * S::group_bytes(T, my);
+  float* tile = reinterpret_cast<float*>(base);
+  cx<f2>* buf = reinterpret_cast<cx<f2>*>(base + ((size_t)Y * T * 4 + 15) / 16 * 16);
+  cx<f2>* Dh = buf + Y;                                             // (2my+1) entries of the current quad
+  cx<float>* D = reinterpret_cast<cx<float>*>(Dh + (2 * my + 1));   // [NKY][TQ*4]
+  FftTwiddles<float, Y> tw;
+  tw.load(twtab, t);
+  CtaSyncS sync;
+  int parity = 0;
+  const int plane = blockIdx.x * GP + g;
+  const bool valid = plane < nplanes;
+  const int pl = valid ? plane : nplanes - 1;
+
+  // t-axis synthesis on the kept ky:  D[kyi][t] = sum_kt Sy[t][kt] Z2[kyi][kt]   (complex)
+  const cx<float>* src = Z2 + (size_t)pl * NKY * mt;
+  for (int j = t; j < NKY * TQ * 4; j += NT) {
+    const int kyi = j / (TQ * 4), tt = j % (TQ * 4);
+    float sr = 0.f, si = 0.f;
+    if (tt < T) {
+      const cx<float>* zr = src + (size_t)kyi * mt;
+      const cx<float>* sy = Sy + (size_t)tt * mt;
+      for (int kt = 0; kt < mt; ++kt) {
+        const cx<float> a = sy[kt], v = zr[kt];
+        sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
+        si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
+      }
+    }
+    D[j] = cx<float>{sr, si};
+  }
+  __syncthreads();
+  for (int q = 0; q < TQ; ++q) {
+    // Hermitian part along ky of the four time samples of this quad, packed two per lane:
+    // lane lo: Dh[t0] + i Dh[t0+1], lane hi: Dh[t0+2] + i Dh[t0+3]   (support: ky in [0,my] u [Y-my,Y-1])
+    for (int e = t; e < 2 * my + 1; e += NT) {
+      const int ky = e <= my ? e : Y - my + (e - my - 1);
+      const int kn = (Y - ky) % Y;
+      const int i1 = kept_index(ky, Y, my), i2 = kept_index(kn, Y, my);
+      cx<float> h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const cx<float> a = i1 >= 0 ? D[(size_t)i1 * TQ * 4 + 4 * q + j] : cx<float>{0.f, 0.f};
+        const cx<float> b = i2 >= 0 ? D[(size_t)i2 * TQ * 4 + 4 * q + j] : cx<float>{0.f, 0.f};
+        h[j] = cx<float>{0.5f * (a.x + b.x), 0.5f * (a.y - b.y)};
+      }
+      // (h0 + i h1, h2 + i h3)
+      Dh[e] = cx<f2>{f2(h[0].x - h[1].y, h[2].x - h[3].y), f2(h[0].y + h[1].x, h[2].y + h[3].x)};
+    }
+    __syncthreads();
+    cx<f2> z[1][8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int ky = t + m * NT;
+      const cx<f2> zero{f2(0.f), f2(0.f)};
+      z[0][m] = ky <= my ? Dh[ky] : (ky >= Y - my ? Dh[my + 1 + ky - (Y - my)] : zero);
+    }
+    fft_run<f2, Y, +1, 1, false, Y>(z, tw, buf, parity, t, sync);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      float* r = tile + (t + m * NT) * T + 4 * q;
+      r[0] = z[0][m].x.lo;
+      if (4 * q + 1 < T) r[1] = z[0][m].y.lo;
+      if (4 * q + 2 < T) r[2] = z[0][m].x.hi;
+      if (4 * q + 3 < T) r[3] = z[0][m].y.hi;
+    }
+    __syncthreads();
+  }
+  if (valid) {
+    float* dst = y + (size_t)plane * Y * T;
+    for (int i = t; i < Y * T; i += NT) dst[i] = tile[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// x-axis transforms on column pairs.  In: FWD  Z [bc][X][ncol]  ->  Xh [bc][2mx][ncol] (kept kx)
+//                                      INV  Yh [bc][2mx][ncol] ->  Z  [bc][X][ncol]  (zero padded)
+// CTA = GP groups of NT = X/8 threads; group g transforms column pair (blockIdx.x * GP + g) of slab
+// blockIdx.y; the [X][GP] tile of 16-byte entries makes the strided side 128-byte rows.
+template <int X>
+struct XaxisSmem {
+  static constexpr int NT = X / 8;
+  static constexpr int GP = (256 / NT) > 8 ? 8 : ((256 / NT) > 0 ? (256 / NT) : 1);
+  static constexpr int RS = GP + 1;  // padded tile row (entries)
+  static constexpr size_t BYTES = (size_t)X * RS * 16 + (size_t)GP * X * 16;
+};
+
+template <int X, bool FWD>
+__global__ void __launch_bounds__(XaxisSmem<X>::GP * (X / 8))
+sconv_xaxis_kernel(const cx<float>* __restrict__ in, cx<float>* __restrict__ out,
+                   const cx<float>* __restrict__ twtab, SconvDims d, int ncol) {
+  typedef XaxisSmem<X> S;
+  constexpr int NT = S::NT, GP = S::GP, RS = S::RS;
+  const int mx = d.mx, NKX = 2 * mx;
+  TCFD_DYN_SMEM(smem_raw);
+  cx<f2>* tile = reinterpret_cast<cx<f2>*>(smem_raw);  // [X][RS]
+  cx<f2>* bufs = tile + (size_t)X * RS;
+  const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+  cx<f2>* buf = bufs + (size_t)g * X;
+  FftTwiddles<float, X> tw;
+  tw.load(twtab, t);
+  CtaSyncS sync;
+  int parity = 0;
+  const int npairs = (ncol + 1) / 2;
+  const int pair0 = blockIdx.x * GP;
+  const size_t slab = blockIdx.y;
+  const int pair = pair0 + g;
+  const int c0 = 2 * pair, c1 = 2 * pair + 1;
+  const bool v0 = pair < npairs, v1 = v0 && c1 < ncol;
+  cx<f2> z[1][8];
+  const cx<f2> zero{f2(0.f), f2(0.f)};
+
+  if (FWD) {
+    // cooperative load of the [X][GP pairs] tile (rows of up to GP*16 contiguous bytes)
+    const cx<float>* src = in + slab * (size_t)X * ncol;
+    for (int i = threadIdx.x; i < X * GP; i += GP * NT) {
+      const int row = i / GP, gg = i % GP, ca = 2 * (pair0 + gg), cb = ca + 1;
+      const cx<float> a = ca < ncol ? src[(size_t)row * ncol + ca] : cx<float>{0.f, 0.f};
+      const cx<float> b = cb < ncol ? src[(size_t)row * ncol + cb] : cx<float>{0.f, 0.f};
+      tile[row * RS + gg] = cx<f2>{f2(a.x, b.x), f2(a.y, b.y)};
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) z[0][m] = tile[(t + m * NT) * RS + g];
+    fft_run<f2, X, -1, 1, false, X>(z, tw, buf, parity, t, sync);
+    cx<float>* dst = out + slab * (size_t)NKX * ncol;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int kxi = kept_index(t + m * NT, X, mx);
+      if (kxi >= 0) {
+        if (v0) dst[(size_t)kxi * ncol + c0] = cx<float>{z[0][m].x.lo, z[0][m].y.lo};
+        if (v1) dst[(size_t)kxi * ncol + c1] = cx<float>{z[0][m].x.hi, z[0][m].y.hi};
+      }
+    }
+  } else {
+    const cx<float>* src = in + slab * (size_t)NKX * ncol;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int kxi = kept_index(t + m * NT, X, mx);
+      z[0][m] = zero;
+      if (kxi >= 0) {
+        const cx<float> a = v0 ? src[(size_t)kxi * ncol + c0] : cx<float>{0.f, 0.f};
+        const cx<float> b = v1 ? src[(size_t)kxi * ncol + c1] : cx<float>{0.f, 0.f};
+        z[0][m] = cx<f2>{f2(a.x, b.x), f2(a.y, b.y)};
+      }
+    }
+    fft_run<f2, X, +1, 1, false, X>(z, tw, buf, parity, t, sync);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) tile[(t + m * NT) * RS + g] = z[0][m];
+    __syncthreads();
+    cx<float>* dst = out + slab * (size_t)X * ncol;
+    for (int i = threadIdx.x; i < X * GP; i += GP * NT) {
+      const int row = i / GP, gg = i % GP, ca = 2 * (pair0 + gg), cb = ca + 1;
+      const cx<f2> v = tile[row * RS + gg];
+      if (ca < ncol) dst[(size_t)row * ncol + ca] = cx<float>{v.x.lo, v.y.lo};
+      if (cb < ncol) dst[(size_t)row * ncol + cb] = cx<float>{v.x.hi, v.y.hi};
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mode mixing.  Modes are indexed k = (kxi * NKY + kyi) * mt + kt; corner = (kxi >= mx) + 2 (kyi >= my);
+// weights of a corner: [Ci][Co][mx][my][mt] complex (the reference's parameter layout).
+struct MixArgs {
+  const cx<float>* w[4];
+  const cx<float>* bias[4];  // [mx][my][mt] or null
+  cx<float>* gw[4];
+  cx<float>* gbias[4];
+  int B, Ci, Co;
+  float delta;
+};
+
+TCFD_HD void mode_split(int k, const SconvDims& d, int& corner, int& widx) {
+  const int kt = k % d.mt, r = k / d.mt, kyi = r % (2 * d.my), kxi = r / (2 * d.my);
+  const int cx_ = kxi >= d.mx, cy = kyi >= d.my;
+  corner = cx_ + 2 * cy;
+  widx = ((kxi - cx_ * d.mx) * d.my + (kyi - cy * d.my)) * d.mt + kt;
+}
+TCFD_D cx<float> cmul(cx<float> a, cx<float> b) {
+  return cx<float>{fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)};
+}
+TCFD_D cx<float> cmul_conj(cx<float> a, cx<float> b) {  // a * conj(b)
+  return cx<float>{fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y))};
+}
+
+constexpr int MIX_BT = 8;  // batch tile held in registers
+
+// Yh[b][o][k] = sum_i Xh[b][i][k] W[i][o][k] (+ delta bias[k]); thread = (k, o), loop over b tiles
+__global__ void __launch_bounds__(128)
+sconv_mix_fwd_kernel(const cx<float>* __restrict__ Xh, cx<float>* __restrict__ Yh, MixArgs a, SconvDims d) {
+  const int K = 4 * d.mx * d.my * d.mt, msz = d.mx * d.my * d.mt;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, o = blockIdx.y;
+  if (k >= K) return;
+  int corner, widx;
+  mode_split(k, d, corner, widx);
+  const cx<float>* w = a.w[corner] + (size_t)o * msz + widx;
+  cx<float> bias{0.f, 0.f};
+  if (a.bias[corner]) {
+    const cx<float> bb = a.bias[corner][widx];
+    bias = cx<float>{a.delta * bb.x, a.delta * bb.y};
+  }
+  for (int b0 = 0; b0 < a.B; b0 += MIX_BT) {
+    cx<float> acc[MIX_BT];
+#pragma unroll
+    for (int j = 0; j < MIX_BT; ++j) acc[j] = cx<float>{0.f, 0.f};
+    for (int i = 0; i < a.Ci; ++i) {
+      const cx<float> wi = w[(size_t)i * a.Co * msz];
+#pragma unroll
+      for (int j = 0; j < MIX_BT; ++j)
+        if (b0 + j < a.B) acc[j] = acc[j] + cmul(Xh[((size_t)(b0 + j) * a.Ci + i) * K + k], wi);
+    }
+#pragma unroll
+    for (int j = 0; j < MIX_BT; ++j)
+      if (b0 + j < a.B) Yh[((size_t)(b0 + j) * a.Co + o) * K + k] = acc[j] + bias;
+  }
+}
+
+// gXh[b][i][k] = sum_o gYh[b][o][k] conj(W[i][o][k]); thread = (k, i)
+__global__ void __launch_bounds__(128)
+sconv_mix_bwd_x_kernel(const cx<float>* __restrict__ gYh, cx<float>* __restrict__ gXh, MixArgs a, SconvDims d) {
+  const int K = 4 * d.mx * d.my * d.mt, msz = d.mx * d.my * d.mt;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (k >= K) return;
+  int corner, widx;
+  mode_split(k, d, corner, widx);
+  const cx<float>* w = a.w[corner] + (size_t)i * a.Co * msz + widx;
+  for (int b0 = 0; b0 < a.B; b0 += MIX_BT) {
+    cx<float> acc[MIX_BT];
+#pragma unroll
+    for (int j = 0; j < MIX_BT; ++j) acc[j] = cx<float>{0.f, 0.f};
+    for (int o = 0; o < a.Co; ++o) {
+      const cx<float> wo = w[(size_t)o * msz];
+#pragma unroll
+      for (int j = 0; j < MIX_BT; ++j)
+        if (b0 + j < a.B) acc[j] = acc[j] + cmul_conj(gYh[((size_t)(b0 + j) * a.Co + o) * K + k], wo);
+    }
+#pragma unroll
+    for (int j = 0; j < MIX_BT; ++j)
+      if (b0 + j < a.B) gXh[((size_t)(b0 + j) * a.Ci + i) * K + k] = acc[j];
+  }
+}
+
+// gW[i][o][k] = sum_b conj(Xh[b][i][k]) gYh[b][o][k]; thread = (k, o), blockIdx.z = i.
+// gbias[k] = delta * sum_{b,o} gYh[b][o][k]  (computed by the i == 0, o == 0 threads)
+__global__ void __launch_bounds__(128)
+sconv_mix_bwd_w_kernel(const cx<float>* __restrict__ Xh, const cx<float>* __restrict__ gYh, MixArgs a, SconvDims d) {
+  const int K = 4 * d.mx * d.my * d.mt, msz = d.mx * d.my * d.mt;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, o = blockIdx.y, i = blockIdx.z;
+  if (k >= K) return;
+  int corner, widx;
+  mode_split(k, d, corner, widx);
+  cx<float> acc{0.f, 0.f};
+  for (int b = 0; b < a.B; ++b) {
+    const cx<float> xv = Xh[((size_t)b * a.Ci + i) * K + k];
+    const cx<float> gv = gYh[((size_t)b * a.Co + o) * K + k];
+    acc = acc + cmul_conj(gv, xv);  // g * conj(x)
+  }
+  a.gw[corner][((size_t)i * a.Co + o) * msz + widx] = acc;
+  if (i == 0 && o == 0 && a.gbias[corner]) {
+    cx<float> s{0.f, 0.f};
+    for (int b = 0; b < a.B; ++b)
+      for (int oo = 0; oo < a.Co; ++oo) s = s + gYh[((size_t)b * a.Co + oo) * K + k];
+    a.gbias[corner][widx] = cx<float>{a.delta * s.x, a.delta * s.y};
+  }
+}
+
+}  // namespace tcfd

@@ -9,6 +9,8 @@
 #define TCFD_D __device__ __forceinline__
 #define TCFD_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define TCFD_LAUNCH3(kernel, gx, gy, gz, block, smem, stream, ...) \
+  kernel<<<dim3((gx), (gy), (gz)), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define TCFD_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #endif
 

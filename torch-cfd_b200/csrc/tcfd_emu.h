@@ -29,6 +29,7 @@ struct emu_dim3 {
 inline thread_local emu_dim3 threadIdx, blockIdx;
 inline emu_dim3 blockDim, gridDim;
 inline unsigned char* emu_smem_ptr = nullptr;
+inline unsigned emu_grid_y = 0, emu_grid_z = 0;
 
 struct EmuBarrier {
   std::mutex m;
@@ -62,6 +63,8 @@ inline void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, F&& bod
   for (unsigned t = 0; t < block; ++t) {
     th.emplace_back([&, t] {
       threadIdx.x = t;
+      blockIdx.y = emu_grid_y;
+      blockIdx.z = emu_grid_z;
       for (unsigned b = 0; b < grid; ++b) {
         blockIdx.x = b;
         body();
@@ -75,6 +78,17 @@ inline void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, F&& bod
 
 #define TCFD_LAUNCH(kernel, grid, block, smem, stream, ...) \
   emu_launch((grid), (block), (smem), [&] { kernel(__VA_ARGS__); })
+// 3-D grids: the y/z block indices are iterated on the host
+#define TCFD_LAUNCH3(kernel, gx, gy, gz, block, smem, stream, ...)          \
+  do {                                                                      \
+    for (unsigned emu_z = 0; emu_z < (unsigned)(gz); ++emu_z)               \
+      for (unsigned emu_y = 0; emu_y < (unsigned)(gy); ++emu_y) {           \
+        emu_grid_y = emu_y; emu_grid_z = emu_z;                             \
+        gridDim.y = (gy); gridDim.z = (gz);                                 \
+        emu_launch((gx), (block), (smem), [&] { kernel(__VA_ARGS__); });    \
+      }                                                                     \
+    emu_grid_y = emu_grid_z = 0; gridDim.y = gridDim.z = 1;                 \
+  } while (0)
 #define TCFD_DYN_SMEM(name) unsigned char* name = emu_smem_ptr
 
 // minimal runtime shims

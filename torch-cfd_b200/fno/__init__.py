@@ -1,0 +1,3 @@
+"""FNO / SFNO spectral-convolution layers backed by the pruned-FFT sm_100a kernels of libtcfd
+(reference: fno/fno3d.py, fno/sfno.py, fno/base.py)."""
+from .spectral_conv import SpectralConv3d, SpectralConvS, SpectralConvT, spectral_conv3d  # noqa: F401
