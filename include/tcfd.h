@@ -98,6 +98,14 @@ int tcfd_ns2d_explicit_terms(tcfd_ns2d_t* h, const void* w_in, void* f_out, int 
 int tcfd_ns2d_residual(tcfd_ns2d_t* h, const void* w_in, const void* wt_in, void* r_out, int batch,
                        void* stream);
 
+/* Recording step of get_trajectory_imex (fno/data_gen/solvers.py:245-256): writes slot `it` of the
+ * device snapshot buffers [batch][n_t][n][n/2+1] (complex64 when out_prec = 32, complex128 when 64):
+ *   snap_w <- w, snap_psi <- -1/laplace' * w (vorticity_to_velocity, torch_cfd/spectral.py:113),
+ *   snap_dwdt <- dwdt, snap_res <- res.  Any snapshot pointer may be NULL. */
+int tcfd_ns2d_record(tcfd_ns2d_t* h, const void* w, const void* dwdt, const void* res, void* snap_w,
+                     void* snap_psi, void* snap_dwdt, void* snap_res, int batch, int n_t, int it, int out_prec,
+                     void* stream);
+
 /* Same as tcfd_ns2d_step but with HOST buffers (pinned memory recommended): uploads w_in,
  * steps, downloads w_out (and dwdt if not NULL) on `stream`, batch-chunked so copies overlap
  * compute.  This is the end-to-end call a host-resident caller makes. */

@@ -187,3 +187,38 @@ def test_fp32_drift_1000_steps_256():
         wr, _ = O.forward(tb, w0, 1e-3, 1000)
         e = rel_l2(torch.fft.irfft2(w.cpu()), torch.fft.irfft2(wr))
         assert e < 1e-3, e
+
+
+def test_get_trajectory_imex_vs_reference_golden():
+    """recorded (w, psi, dw/dt, residual), complex64, (B, n_t, n, nh), CPU result."""
+    import torch_cfd_b200 as T
+    g = load_golden("ns2d_c1_fp64")
+    with default_dtype(torch.float64):
+        ns = _module_from_golden(g, torch.float64)
+        w0 = torch.from_numpy(g["w0_hat"]).to(DEV)
+        out = T.get_trajectory_imex(ns, w0, float(g["dt"]), num_steps=int(g["traj_num_steps"]),
+                                    record_every_steps=int(g["traj_every"]))
+        for k in ("vorticity", "stream", "vort_t", "residual"):
+            ref = torch.from_numpy(g[f"traj_{k}"])
+            assert out[k].shape == ref.shape and out[k].dtype == torch.complex64 and not out[k].is_cuda
+            if k == "residual":
+                err = (torch.linalg.norm(out[k] - ref) / np.linalg.norm(g["traj_vort_t"])).item()
+            else:
+                err = rel_l2(out[k], ref)
+            assert err < 2e-7, (k, err)
+        dev = T.get_trajectory_imex(ns, w0, float(g["dt"]), num_steps=3, fields=("vorticity",), device_result=True)
+        assert set(dev) == {"vorticity"} and dev["vorticity"].is_cuda and dev["vorticity"].shape[-3] == 3
+
+
+def test_trajectory_fp32_batch_vs_oracle():
+    import torch_cfd_b200 as T
+    n, dtype = 128, torch.float32
+    with default_dtype(dtype):
+        ns = build_module(n, dtype, 1e-3, 0.1, "vorticity")
+        tb = oracle_tables(n, dtype, 1e-3, 0.1, "vorticity")
+        w0 = O.synthetic_vorticity_hat(n, 3, 4, dtype)
+        out = T.get_trajectory_imex(ns, w0.to(DEV), 1e-3, num_steps=9, record_every_steps=4)
+        ref = O.trajectory(tb, w0, 1e-3, 9, 4)
+        for k in ("vorticity", "stream", "vort_t"):
+            assert out[k].shape == ref[k].shape == (3, 3, n, n // 2 + 1)
+            assert rel_l2(out[k], ref[k]) < (2e-5 if k != "vort_t" else 2e-2), k

@@ -64,6 +64,7 @@ class TcfdLibrary:
                                            ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
         c.tcfd_ns2d_explicit_terms.argtypes = [vp, vp, vp, ci, vp]
         c.tcfd_ns2d_residual.argtypes = [vp, vp, vp, vp, ci, vp]
+        c.tcfd_ns2d_record.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
         pp = ctypes.POINTER(vp)
         c.tcfd_sconv3d_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_SconvDesc)]
         c.tcfd_sconv3d_destroy.argtypes = [vp]
@@ -196,6 +197,18 @@ class NS2DPlan:
             res[k] = {"launches": cnt[i], "ms_total": ms[i],
                       "us_per_launch": (1e3 * ms[i] / cnt[i]) if cnt[i] else None}
         return res
+
+    def record(self, w, dwdt, res, snaps, it: int):
+        """snaps: dict with (B, n_t, n, nh) complex tensors (or None) under vorticity/stream/vort_t/residual."""
+        self._check_state(w, "w")
+        first = next(v for v in snaps.values() if v is not None)
+        n_t = first.shape[1]
+        out_prec = 32 if first.dtype == torch.complex64 else 64
+        ptr = lambda t: None if t is None else t.data_ptr()
+        rc = self.lib.c.tcfd_ns2d_record(self._h, w.data_ptr(), ptr(dwdt), ptr(res), ptr(snaps.get("vorticity")),
+                                         ptr(snaps.get("stream")), ptr(snaps.get("vort_t")), ptr(snaps.get("residual")),
+                                         w.shape[0], n_t, int(it), out_prec, _stream_handle(w))
+        self.lib.check(rc, "tcfd_ns2d_record")
 
     def explicit_terms(self, w_in: torch.Tensor, out: torch.Tensor):
         self._check_state(w_in, "w_in")

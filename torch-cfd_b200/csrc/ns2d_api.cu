@@ -506,6 +506,48 @@ extern "C" int tcfd_ns2d_residual(tcfd_ns2d_t* h, const void* w_in, const void* 
                        : eval_impl<double>(h, tcfd::UPD_RESID, w_in, wt_in, r_out, batch, stream);
 }
 
+namespace {
+template <class T, class O>
+int record_impl(tcfd_ns2d* h, const void* w, const void* dwdt, const void* res, void* sw, void* spsi, void* sdw,
+                void* sres, int batch, int n_t, int it, void* stream) {
+  const size_t per = (size_t)h->n * h->nh, total = per * batch;
+  const int threads = 256;
+  size_t blocks = (total + threads - 1) / threads;
+  const size_t cap = (size_t)h->num_sms * 8;
+#ifndef TCFD_EMU
+  if (blocks > cap) blocks = cap;
+#else
+  (void)cap;
+  if (blocks > 4) blocks = 4;
+#endif
+  TCFD_LAUNCH((tcfd::ns2d_record_kernel<T, O>), (unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream),
+              static_cast<const tcfd::cx<T>*>(w), static_cast<const tcfd::cx<T>*>(dwdt),
+              static_cast<const tcfd::cx<T>*>(res), static_cast<const T*>(h->nil), static_cast<tcfd::cx<O>*>(sw),
+              static_cast<tcfd::cx<O>*>(spsi), static_cast<tcfd::cx<O>*>(sdw), static_cast<tcfd::cx<O>*>(sres), per, n_t, it,
+              total);
+  h->launches++;
+#ifndef TCFD_EMU
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TCFD_ERR_CUDA, std::string("record kernel: ") + cudaGetErrorString(e));
+#endif
+  return 0;
+}
+}  // namespace
+
+extern "C" int tcfd_ns2d_record(tcfd_ns2d_t* h, const void* w, const void* dwdt, const void* res, void* snap_w,
+                                void* snap_psi, void* snap_dwdt, void* snap_res, int batch, int n_t, int it,
+                                int out_prec, void* stream) {
+  if (!h || !w) return fail(TCFD_ERR_INVALID, "null argument");
+  if (batch < 1 || n_t < 1 || it < 0 || it >= n_t) return fail(TCFD_ERR_INVALID, "bad batch / n_t / it");
+  if ((snap_dwdt && !dwdt) || (snap_res && !res)) return fail(TCFD_ERR_INVALID, "snapshot requested without its source");
+  if (out_prec != 32 && out_prec != 64) return fail(TCFD_ERR_INVALID, "out_prec must be 32 or 64");
+  if (h->prec == 32)
+    return out_prec == 32 ? record_impl<float, float>(h, w, dwdt, res, snap_w, snap_psi, snap_dwdt, snap_res, batch, n_t, it, stream)
+                          : record_impl<float, double>(h, w, dwdt, res, snap_w, snap_psi, snap_dwdt, snap_res, batch, n_t, it, stream);
+  return out_prec == 32 ? record_impl<double, float>(h, w, dwdt, res, snap_w, snap_psi, snap_dwdt, snap_res, batch, n_t, it, stream)
+                        : record_impl<double, double>(h, w, dwdt, res, snap_w, snap_psi, snap_dwdt, snap_res, batch, n_t, it, stream);
+}
+
 extern "C" int tcfd_ns2d_step_host(tcfd_ns2d_t* h, const void* w_in_host, void* w_out_host, void* dwdt_host,
                                    int batch, int steps, int nstages, const double* beta, const double* gdt,
                                    const double* mu, double inv_total_dt, void* stream_) {

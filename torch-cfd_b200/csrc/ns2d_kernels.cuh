@@ -71,6 +71,27 @@ struct NsParams {
   T beta, gdt, mu, inv_tdt;
 };
 
+// trajectory recording (fno/data_gen/solvers.py:245-256): cast w, psi = nil * w, dw/dt and the residual
+// of one recorded step into slot `it` of the (B, n_t, n, nh) snapshot buffers
+template <class T, class O>
+__global__ void ns2d_record_kernel(const cx<T>* __restrict__ w, const cx<T>* __restrict__ dwdt,
+                                   const cx<T>* __restrict__ res, const T* __restrict__ nil, cx<O>* sw, cx<O>* spsi,
+                                   cx<O>* sdw, cx<O>* sres, size_t per, int n_t, int it, size_t total) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = idx / per, e = idx % per;
+    const size_t o = (b * n_t + it) * per + e;
+    const cx<T> wv = w[idx];
+    if (sw) sw[o] = cx<O>{(O)wv.x, (O)wv.y};
+    if (spsi) {
+      const T f = nil[e];
+      spsi[o] = cx<O>{(O)(f * wv.x), (O)(f * wv.y)};
+    }
+    if (sdw) sdw[o] = cx<O>{(O)dwdt[idx].x, (O)dwdt[idx].y};
+    if (sres) sres[o] = cx<O>{(O)res[idx].x, (O)res[idx].y};
+  }
+}
+
 struct CtaSync {
   TCFD_D void operator()() const { __syncthreads(); }
 };

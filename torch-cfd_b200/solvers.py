@@ -1,0 +1,116 @@
+"""``get_trajectory_imex`` (reference: fno/data_gen/solvers.py:191-265) on the fused CUDA step, plus the
+batch-sharded multi-GPU form with the path's single collective (an all-gather of the recorded fields).
+
+Reference semantics kept: the state is stepped ``num_steps`` times; after every step ``t`` with
+``t % record_every_steps == 0`` the tuple (w, psi, dw/dt of that step, residual(w, dw/dt)) is recorded,
+cast to ``dtype`` (complex64 by default even for fp64 runs) and stacked on dim -3; the result is a
+dict ``vorticity, stream, vort_t, residual`` of CPU tensors.  Differences: steps after the last
+recorded one are not executed (their result is never returned upstream either), the snapshots are
+written by one kernel into device buffers and leave the GPU in ONE copy at the end instead of one
+synchronising ``.cpu()`` per field per snapshot, and the upstream NameError (``tqdm`` is never
+imported there) is not reproduced.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from .equations import NavierStokes2DSpectral, RK4CrankNicolsonStepper
+
+FIELDS = ("vorticity", "stream", "vort_t", "residual")
+
+
+def _record_steps(num_steps: int, record_every_steps: int):
+    return list(range(0, num_steps, record_every_steps))
+
+
+def _trajectory_device(equation, w0, dt, num_steps, record_every_steps, dtype, fields, pbar, pbar_desc):
+    """Snapshots on the device of ``w0``: dict field -> (B, n_t, n, nh) tensor of ``dtype``."""
+    rec = _record_steps(num_steps, record_every_steps)
+    n_t = len(rec)
+    fused = isinstance(equation, NavierStokes2DSpectral) and isinstance(equation.solver, RK4CrankNicolsonStepper) \
+        and w0.is_cuda
+    n, nh = w0.shape[-2:]
+    w = w0.detach().reshape(-1, n, nh).contiguous()
+    B = w.shape[0]
+    snaps = {k: (torch.empty(B, n_t, n, nh, dtype=dtype, device=w.device) if k in fields else None) for k in FIELDS}
+    bar = None
+    if pbar:
+        try:
+            from tqdm import tqdm
+            bar = tqdm(total=num_steps, desc=pbar_desc)
+        except ImportError:
+            bar = None
+    done = -1
+    for it, t_step in enumerate(rec):
+        gap = t_step - done - 1          # un-recorded steps before this one
+        if fused:
+            if gap > 0:
+                w, _ = equation._fused_steps(w, dt, gap, equation.solver, want_dudt=False)
+            w, dwdt = equation._fused_steps(w, dt, 1, equation.solver)
+            res = equation.residual(w, dwdt) if snaps["residual"] is not None else None
+            plan = equation._plan(w.device, B)
+            with torch.cuda.device(w.device):
+                plan.record(w, dwdt, res, snaps, it)
+        else:  # any ImplicitExplicitODE-like object (used by the CPU tests with an oracle-backed equation)
+            for _ in range(gap):
+                w, _ = equation.forward(w, dt=dt)
+            w, dwdt = equation.forward(w, dt=dt)
+            vals = {"vorticity": w, "vort_t": dwdt}
+            if snaps["stream"] is not None:
+                vals["stream"] = equation.stream_function(w)
+            if snaps["residual"] is not None:
+                vals["residual"] = equation.residual(w, dwdt)
+            for k, v in vals.items():
+                if snaps[k] is not None:
+                    snaps[k][:, it] = v.detach().to(dtype)
+        done = t_step
+        if bar is not None:
+            bar.update(gap + 1)
+    if bar is not None:
+        bar.close()
+    return {k: v for k, v in snaps.items() if v is not None}
+
+
+def get_trajectory_imex(equation, w0: torch.Tensor, dt: float, num_steps: int = 1, record_every_steps: int = 1,
+                        pbar: bool = False, pbar_desc: str = "generating trajectories using RK4",
+                        require_grad: bool = False, dtype: torch.dtype = torch.complex64,
+                        fields: Sequence[str] = FIELDS, device_result: bool = False) -> Dict[str, torch.Tensor]:
+    """Same signature and return value as the reference (plus ``fields`` / ``device_result``)."""
+    if require_grad:
+        raise NotImplementedError("torch-cfd_b200: the fused step is inference-only (SURVEY 8b)")
+    lead = w0.shape[:-2]
+    n, nh = w0.shape[-2:]
+    with torch.no_grad():
+        snaps = _trajectory_device(equation, w0, dt, num_steps, record_every_steps, dtype, tuple(fields), pbar, pbar_desc)
+    out = {}
+    for k, v in snaps.items():
+        v = v.reshape(*lead, v.shape[1], n, nh)
+        out[k] = v if device_result else v.cpu()
+    return out
+
+
+def get_trajectory_imex_sharded(equation, w0_local: torch.Tensor, dt: float, num_steps: int = 1,
+                                record_every_steps: int = 1, dtype: torch.dtype = torch.complex64,
+                                fields: Sequence[str] = ("vorticity",), group=None,
+                                device_result: bool = False) -> Dict[str, torch.Tensor]:
+    """Multi-GPU trajectory: one process per GPU, each stepping ITS contiguous slice ``w0_local`` of
+    the global batch (samples never interact: no halo, no data-path collective), followed by the
+    path's only collective -- ``all_gather_into_tensor`` of the recorded fields (NCCL over NVLink on
+    GPUs, gloo in the CPU tests).  Every rank returns the global (B_total, n_t, n, nh) tensors, ranks
+    ordered along the batch axis.  All ranks must hold the same local batch size."""
+    import torch.distributed as dist
+    with torch.no_grad():
+        snaps = _trajectory_device(equation, w0_local, dt, num_steps, record_every_steps, dtype, tuple(fields), False, "")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return {k: (v if device_result else v.cpu()) for k, v in snaps.items()}
+    world = dist.get_world_size(group)
+    out = {}
+    for k, v in snaps.items():
+        real = torch.view_as_real(v.contiguous())
+        gathered = torch.empty((world * real.shape[0],) + tuple(real.shape[1:]), dtype=real.dtype, device=real.device)
+        dist.all_gather_into_tensor(gathered, real, group=group)
+        g = torch.view_as_complex(gathered)
+        out[k] = g if device_result else g.cpu()
+    return out
