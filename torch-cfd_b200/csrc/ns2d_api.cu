@@ -367,9 +367,11 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
   int rc = (d->prec == 32) ? create_tables<float>(h, d) : create_tables<double>(h, d);
   if (rc == 0 && d->f_hat) rc = tcfd_ns2d_set_forcing(h, d->f_hat);
   if (rc == 0) {
-    // chunk: the per-chunk working set (H = 4 spectra-sized complex fields per sample dominates)
-    // is kept under TCFD_CHUNK_MB (default 40 MB) so that it stays L2-resident between launches
-    double budget_mb = 40.0;
+    // chunk: samples per launch.  Default = the whole batch: with two launches per substage a
+    // chunk small enough to keep H L2-resident (~8 samples at 512^2) under-fills the 148 SMs and
+    // loses more than the saved DRAM traffic (measured: profiles/r01 chunk sweep).  TCFD_CHUNK_MB
+    // caps the per-chunk working set for experiments.
+    double budget_mb = 1e9;
     if (const char* e = getenv("TCFD_CHUNK_MB")) budget_mb = atof(e) > 0 ? atof(e) : budget_mb;
     const double per_sample_mb = (double)h->nh * h->n * 2 * h->es * 8.0 / 1e6;  // H(4) + advt + w, h, wS
     int chunk = (int)(budget_mb / per_sample_mb);
