@@ -144,7 +144,7 @@ def run_reference(a):
     v, el = cpu_reference_steps_per_s(a.n, a.batch, dtype, k, threads)
     sample = f"{k} full steps of the {a.batch} x {a.n}^2 batch after 1 warm-up step, torch CPU, {threads} threads"
     unit = f"steps/s (one step = {a.batch} x {a.n}^2 samples, RK4+CN)"
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": "rk4_spectral_steps_per_sec", "value": v, "unit": unit,
         "n_gpus": a.gpus, "steps": k, "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "f64",
@@ -289,10 +289,19 @@ def run_ours(a):
         out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
                                "sample": f"{a.cpu_steps} full steps of the {B} x {n}^2 batch after 1 warm-up, "
                                          f"oracle port of the reference (torch CPU), {el:.1f} s"}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
+
+
+def _emit(line: str):
+    os.write(_REAL_STDOUT, (line + "\n").encode())
 
 
 if __name__ == "__main__":
+    # the contract is ONE JSON line on stdout: anything native libraries print there (NCCL prints its
+    # version banner to stdout) is sent to stderr instead
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

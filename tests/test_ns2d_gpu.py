@@ -222,3 +222,16 @@ def test_trajectory_fp32_batch_vs_oracle():
         for k in ("vorticity", "stream", "vort_t"):
             assert out[k].shape == ref[k].shape == (3, 3, n, n // 2 + 1)
             assert rel_l2(out[k], ref[k]) < (2e-5 if k != "vort_t" else 2e-2), k
+
+
+def test_forward_host_pipeline_equals_device_forward():
+    """The host-buffer entry point (chunked upload | step | download pipeline) returns bit-identical
+    results to the device-resident forward, for batches that do and do not divide into the chunks."""
+    n, dtype = 128, torch.float32
+    with default_dtype(dtype):
+        ns = build_module(n, dtype, 1e-3, 0.1, "vorticity")
+        for b in (1, 3, 10):
+            w0 = O.synthetic_vorticity_hat(n, b, 6, dtype)
+            wd, dd = ns(w0.to(DEV), 1e-3, steps=2)
+            wh, dh = ns.forward_host(w0.pin_memory(), 1e-3, steps=2)
+            assert not wh.is_cuda and torch.equal(wh, wd.cpu()) and torch.equal(dh, dd.cpu())

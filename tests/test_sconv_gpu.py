@@ -119,3 +119,26 @@ def test_errors_on_gpu():
         m(torch.zeros(1, 2, 32, 32, 16, device=DEV, dtype=torch.float64))
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 32, 32, 16, device=DEV))
+
+
+def test_fno3d_forward_matches_reference_structure():
+    """C5's model on a reduced batch: FNO3d(8, 8, 5, width 20) on (2, 13, 128, 128, 10); every
+    spectral layer replaced by the oracle must give the same output (1e-5), state_dict keys as upstream."""
+    from torch_cfd_b200.fno import FNO3d
+    torch.manual_seed(11)
+    m = FNO3d(8, 8, 5, 20, input_channel=10).to(DEV).eval()
+    keys = set(m.state_dict().keys())
+    assert {"p.weight", "spectral_conv.0.weights1", "spectral_conv.3.weights4", "mlp.0.mlp1.weight", "w.3.bias",
+            "q.mlp2.weight"} <= keys
+    x = torch.randn(2, 13, 128, 128, 10, device=DEV)
+    with torch.no_grad():
+        y, aux = m(x)
+        assert aux is None and y.shape == (2, 128, 128, 10)
+        # same network with the spectral layers evaluated by the oracle on the CPU
+        h = m.p(x)
+        for conv, mlp, w, act in zip(m.spectral_conv, m.mlp, m.w, m.activation):
+            ws = [getattr(conv, f"weights{i}").detach().cpu() for i in range(1, 5)]
+            h1 = SO.spectral_conv3d(h.cpu(), ws, 8, 8, 5).to(DEV)
+            h = act(mlp(h1) + w(h))
+        yr = m.q(h).squeeze(1)
+        assert rel_l2(y, yr) < 1e-5

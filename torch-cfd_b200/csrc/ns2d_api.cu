@@ -55,6 +55,10 @@ struct tcfd_ns2d {
   void *hA = nullptr, *hB = nullptr, *wS = nullptr, *wT = nullptr, *H = nullptr, *advt = nullptr;
   void *stage_in = nullptr, *stage_out = nullptr, *stage_dw = nullptr;  // step_host staging
   tcfd::TileMaps maps{};  // TMA descriptors of the H tiles (second-generation cols kernel)
+  // step_host pipeline: copy-in / copy-out streams and per-chunk events
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done, ev_free;
+  cudaEvent_t ev_start = nullptr, ev_end = nullptr;
   size_t ws_bytes = 0;
   int launches = 0;
   // measurement mode (tcfd_ns2d_step_timed): every launch is bracketed by events
@@ -374,9 +378,9 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
     double budget_mb = 1e9;
     if (const char* e = getenv("TCFD_CHUNK_MB")) budget_mb = atof(e) > 0 ? atof(e) : budget_mb;
     const double per_sample_mb = (double)h->nh * h->n * 2 * h->es * 8.0 / 1e6;  // H(4) + advt + w, h, wS
-    int chunk = (int)(budget_mb / per_sample_mb);
+    const double want = budget_mb / per_sample_mb;
+    int chunk = want >= (double)h->max_batch ? h->max_batch : (int)want;
     if (chunk < 1) chunk = 1;
-    if (chunk > h->max_batch) chunk = h->max_batch;
     h->chunk = chunk;
     const size_t sb = h->state_bytes(h->chunk);
     // advt: v1 [B][nh][n] complex; v2 [B][n/4+1][n][4 reals] (slightly larger)
@@ -415,6 +419,12 @@ extern "C" int tcfd_ns2d_destroy(tcfd_ns2d_t* h) {
                  h->wS, h->H, h->advt, h->stage_in, h->stage_out, h->stage_dw};
   for (void* p : all)
     if (p) cudaFree(p);
+  for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_end) cudaEventDestroy(h->ev_end);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
   return TCFD_OK;
 }
@@ -561,12 +571,51 @@ extern "C" int tcfd_ns2d_step_host(tcfd_ns2d_t* h, const void* w_in_host, void* 
   if (!h->stage_in) { CUDA_TRY(cudaMalloc(&h->stage_in, sb)); h->ws_bytes += sb; }
   if (!h->stage_out) { CUDA_TRY(cudaMalloc(&h->stage_out, sb)); h->ws_bytes += sb; }
   if (dwdt_host && !h->stage_dw) { CUDA_TRY(cudaMalloc(&h->stage_dw, sb)); h->ws_bytes += sb; }
-  const size_t nb = h->state_bytes(batch);
-  CUDA_TRY(cudaMemcpyAsync(h->stage_in, w_in_host, nb, cudaMemcpyHostToDevice, stream));
-  rc = tcfd_ns2d_step(h, h->stage_in, h->stage_out, dwdt_host ? h->stage_dw : nullptr, batch, steps, nstages,
-                      beta, gdt, mu, inv_total_dt, stream_);
-  if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(w_out_host, h->stage_out, nb, cudaMemcpyDeviceToHost, stream));
-  if (dwdt_host) CUDA_TRY(cudaMemcpyAsync(dwdt_host, h->stage_dw, nb, cudaMemcpyDeviceToHost, stream));
+  // Three-stage pipeline over sub-batches: upload (copy-in stream) | step (caller's stream) | download
+  // (copy-out stream).  PCIe is full duplex, so the uploads of chunk c+1 and the downloads of chunk
+  // c-1 run under the kernels of chunk c; the caller's stream finally waits for the last download.
+  int nchunks = 8;
+  if (const char* e = getenv("TCFD_HOST_CHUNKS")) nchunks = atoi(e) > 0 ? atoi(e) : nchunks;
+  if (nchunks > batch) nchunks = batch;
+  if (!h->s_in) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_end, cudaEventDisableTiming));
+  }
+  while ((int)h->ev_in.size() < nchunks) {
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    h->ev_in.push_back(a);
+    h->ev_done.push_back(b);
+  }
+  // the staging buffers may still be in use by work queued earlier on the caller's stream
+  CUDA_TRY(cudaEventRecord(h->ev_start, stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_start, 0));
+  const size_t per = (size_t)h->n * h->nh * 2 * h->es;  // bytes per sample
+  const int base = batch / nchunks, extra = batch % nchunks;
+  int b0 = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const int cb = base + (c < extra ? 1 : 0);
+    const size_t off = (size_t)b0 * per, nb = (size_t)cb * per;
+    unsigned char* din = static_cast<unsigned char*>(h->stage_in) + off;
+    unsigned char* dout = static_cast<unsigned char*>(h->stage_out) + off;
+    unsigned char* ddw = dwdt_host ? static_cast<unsigned char*>(h->stage_dw) + off : nullptr;
+    CUDA_TRY(cudaMemcpyAsync(din, static_cast<const unsigned char*>(w_in_host) + off, nb, cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(cudaEventRecord(h->ev_in[c], h->s_in));
+    CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_in[c], 0));
+    rc = tcfd_ns2d_step(h, din, dout, ddw, cb, steps, nstages, beta, gdt, mu, inv_total_dt, stream_);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_done[c], stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_done[c], 0));
+    CUDA_TRY(cudaMemcpyAsync(static_cast<unsigned char*>(w_out_host) + off, dout, nb, cudaMemcpyDeviceToHost, h->s_out));
+    if (dwdt_host)
+      CUDA_TRY(cudaMemcpyAsync(static_cast<unsigned char*>(dwdt_host) + off, ddw, nb, cudaMemcpyDeviceToHost, h->s_out));
+    b0 += cb;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_end, h->s_out));
+  CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_end, 0));
   return TCFD_OK;
 }
