@@ -66,6 +66,10 @@ int tcfd_ns2d_destroy(tcfd_ns2d_t* h);
 int tcfd_ns2d_set_forcing(tcfd_ns2d_t* h, const void* f_hat);
 /* bytes of device workspace owned by the handle */
 size_t tcfd_ns2d_workspace_bytes(const tcfd_ns2d_t* h);
+/* 0, or TCFD_ERR_CUDA when a kernel of an earlier (asynchronous) call on this handle reported a
+ * failure through the handle's host-visible error word; meaningful after the stream was synchronised.
+ * Every tcfd_ns2d_step call performs this check on entry. */
+int tcfd_ns2d_check(const tcfd_ns2d_t* h);
 /* number of kernel launches the last tcfd_ns2d_* compute call enqueued */
 int tcfd_ns2d_last_launch_count(const tcfd_ns2d_t* h);
 

@@ -69,6 +69,30 @@ def test_emu_kernels_vs_oracle(n, batch, dtype, forcing, smooth):
     assert rel_l2(out, ref) < (1e-12 if dtype == torch.float64 else 2e-6)
 
 
+def test_emu_flow_schedule_matches_two_launch_schedule(monkeypatch):
+    """The persistent dataflow schedule (ns2d_flow.cuh: one launch per call, chunk-major tickets,
+    W-slot workspaces re-used from chunk to chunk) against the two-launch schedule: bit-identical
+    state and dw/dt, with the batch spanning several chunks (3 samples, W = 2 and W = 1)."""
+    n, batch, dtype = 256, 3, torch.float32
+    tb = oracle_tables(n, dtype, 1e-3, 0.1, "vorticity", True)
+    w0 = O.synthetic_vorticity_hat(n, batch, 7, dtype)
+    beta, gdt, mu = substage_scalars(dtype, 1e-3)
+    res = {}
+    for flow, W in [("0", "1"), ("1", "2"), ("1", "1")]:
+        monkeypatch.setenv("TCFD_FLOW", flow)
+        monkeypatch.setenv("TCFD_FLOW_W", W)
+        plan = emu_plan(tb, batch, dtype)
+        out, dw = torch.empty_like(w0), torch.empty_like(w0)
+        plan.step(w0, out, dw, 1, beta, gdt, mu, 1e3)
+        assert plan.last_launch_count == (1 if flow == "1" else 11)
+        res[(flow, W)] = (out, dw)
+        plan.close()
+    for key in [("1", "2"), ("1", "1")]:
+        assert torch.equal(res[key][0], res[("0", "1")][0]) and torch.equal(res[key][1], res[("0", "1")][1])
+    ref, _ = O.forward(tb, w0, 1e-3, 1)
+    assert rel_l2(res[("1", "2")][0], ref) < 2e-6
+
+
 def test_emu_batch_smaller_than_plan_and_errors():
     tb = oracle_tables(32, torch.float32)
     plan = emu_plan(tb, 4, torch.float32)

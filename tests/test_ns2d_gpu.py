@@ -235,3 +235,28 @@ def test_forward_host_pipeline_equals_device_forward():
             wd, dd = ns(w0.to(DEV), 1e-3, steps=2)
             wh, dh = ns.forward_host(w0.pin_memory(), 1e-3, steps=2)
             assert not wh.is_cuda and torch.equal(wh, wd.cpu()) and torch.equal(dh, dd.cpu())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,batch,W", [(256, 20, 64), (256, 20, 6), (512, 12, 5), (512, 12, 64), (1024, 3, 2)])
+def test_flow_schedule_bit_identical_to_two_launch_schedule(n, batch, W, monkeypatch):
+    """Persistent dataflow schedule (one launch per call, per-sample dependency counters, W-slot
+    workspaces) vs the two-launch schedule on the same inputs: bit-identical w and dw/dt for a
+    single-step and a multi-step call, with the batch spanning several chunks (slot re-use)."""
+    dtype = torch.float32
+    w0 = O.synthetic_vorticity_hat(n, batch, 5, dtype).to(DEV)
+    outs = {}
+    for flow in ("0", "1"):
+        monkeypatch.setenv("TCFD_FLOW", flow)
+        monkeypatch.setenv("TCFD_FLOW_W", str(W))
+        with default_dtype(dtype):
+            ns = build_module(n, dtype, 1e-3, 0.1, "vorticity")
+            a = ns(w0, 1e-3, steps=1)
+            b = ns(w0, 1e-3, steps=3)
+            torch.cuda.synchronize()
+            outs[flow] = (a, b, ns._plans[0].last_launch_count)
+            ns.invalidate_plan()
+    assert outs["1"][2] == 1 and outs["0"][2] > 1
+    for k in range(2):
+        for i in range(2):
+            assert torch.equal(outs["0"][k][i], outs["1"][k][i])

@@ -58,6 +58,8 @@ class TcfdLibrary:
         c.tcfd_ns2d_workspace_bytes.argtypes = [vp]
         c.tcfd_ns2d_workspace_bytes.restype = ctypes.c_size_t
         c.tcfd_ns2d_last_launch_count.argtypes = [vp]
+        c.tcfd_ns2d_check.argtypes = [vp]
+        c.tcfd_ns2d_check.restype = ctypes.c_int
         c.tcfd_ns2d_step.argtypes = [vp, vp, vp, vp, ci, ci, ci, dp, dp, dp, ctypes.c_double, vp]
         c.tcfd_ns2d_step_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, dp, dp, dp, ctypes.c_double, vp]
         c.tcfd_ns2d_step_timed.argtypes = [vp, vp, vp, ci, ci, ci, dp, dp, dp, vp,
@@ -150,6 +152,11 @@ class NS2DPlan:
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.c.tcfd_ns2d_last_launch_count(self._h))
+
+    def check(self):
+        """Raise if a kernel of an earlier asynchronous call reported a failure (tcfd_ns2d_check);
+        meaningful after the stream was synchronised."""
+        self.lib.check(self.lib.c.tcfd_ns2d_check(self._h), "tcfd_ns2d_check")
 
     def set_forcing(self, f_hat: Optional[torch.Tensor]):
         if f_hat is None:

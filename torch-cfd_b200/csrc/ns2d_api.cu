@@ -8,7 +8,7 @@
 #include <vector>
 
 #include "../../include/tcfd.h"
-#include "ns2d_kernels.cuh"
+#include "ns2d_flow.cuh"
 #include "ns2d_plan.h"
 #include "tma.cuh"
 #ifndef TCFD_EMU
@@ -61,6 +61,11 @@ struct tcfd_ns2d {
   cudaEvent_t ev_start = nullptr, ev_end = nullptr;
   size_t ws_bytes = 0;
   int launches = 0;
+  // third-generation persistent dataflow schedule (ns2d_flow.cuh)
+  bool flow = false;
+  int* sync_dev = nullptr;   // ticket + per-sample counters
+  int* err_host = nullptr;   // mapped pinned word the kernel raises on a dependency time-out
+  int* err_dev = nullptr;
   // measurement mode (tcfd_ns2d_step_timed): every launch is bracketed by events
   bool timed = false;
   std::vector<cudaEvent_t> ev;
@@ -311,6 +316,57 @@ int step_impl(tcfd_ns2d* h, const void* w_in_, void* w_out_, void* dwdt_, int ba
   return 0;
 }
 
+// One persistent launch for the whole call (ns2d_flow.cuh): chunk-major dataflow schedule.
+template <class T>
+int flow_step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int batch, int steps, int nstages,
+                   const double* beta, const double* gdt, const double* mu, double inv_total_dt, void* stream) {
+  typedef tcfd::cx<T> C;
+  typedef tcfd::cx<typename tcfd::pack2<T>::type> CU;
+  tcfd::FlowParams<T> fp;
+  std::memset(&fp, 0, sizeof(fp));
+  fill_params<T>(h, fp.p, batch);
+  fp.p.mode = tcfd::UPD_RK;
+  fp.p.w_in = static_cast<const C*>(w_in);
+  fp.p.w_out = static_cast<C*>(w_out);
+  if (dwdt) {
+    fp.p.w_old = static_cast<const C*>(w_in);
+    fp.p.dwdt = static_cast<C*>(dwdt);
+    fp.p.inv_tdt = (T)inv_total_dt;
+    fp.w0U = static_cast<CU*>(h->wT);
+  }
+  fp.nsub = steps * nstages;
+  fp.nstages = nstages;
+  fp.W = h->chunk;
+  for (int k = 0; k < nstages; ++k) {
+    fp.beta[k] = (T)beta[k];
+    fp.gdt[k] = (T)gdt[k];
+    fp.mu[k] = (T)mu[k];
+    fp.rd_h[k] = (k > 0 && beta[k] != 0.0) ? 1 : 0;
+    fp.wr_h[k] = (k + 1 < nstages && beta[k + 1] != 0.0) ? 1 : 0;
+  }
+  fp.wU = static_cast<CU*>(h->wS);
+  fp.hU = static_cast<CU*>(h->hA);
+  fp.sync = h->sync_dev;
+  fp.err = h->err_dev;
+  CUDA_TRY(cudaMemsetAsync(h->sync_dev, 0, sizeof(int) * (2 + 2 * (size_t)h->max_batch), static_cast<cudaStream_t>(stream)));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timed) {
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, static_cast<cudaStream_t>(stream)));
+  }
+  const int rc = h->entry.launch_flow(&fp, &h->maps, h->num_sms, stream);
+  if (h->timed) {
+    CUDA_TRY(cudaEventRecord(e1, static_cast<cudaStream_t>(stream)));
+    h->ev.push_back(e0);
+    h->ev.push_back(e1);
+    h->ev_kind.push_back(TCFD_K_ROWS_FULL);
+  }
+  h->launches++;
+  if (rc != 0) return fail(TCFD_ERR_CUDA, std::string("flow kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+  return 0;
+}
+
 template <class T>
 int eval_impl(tcfd_ns2d* h, int mode, const void* w_in, const void* wt_in, void* out, int batch, void* stream) {
   typedef tcfd::cx<T> C;
@@ -381,6 +437,23 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
     const double want = budget_mb / per_sample_mb;
     int chunk = want >= (double)h->max_batch ? h->max_batch : (int)want;
     if (chunk < 1) chunk = 1;
+    // Persistent dataflow schedule (default for N >= 256; TCFD_FLOW=0 selects the two-launch
+    // schedule): the workspaces hold W samples (TCFD_FLOW_W).  Measured on B200 (profiles/r04_*): the
+    // step is latency/issue bound, not DRAM bound, so a window small enough to stay L2-resident
+    // (W ~ 8 at 512^2) loses more to dependency stalls than it saves in DRAM traffic; default W = 64.
+    h->flow = h->entry.launch_flow != nullptr;
+    if (const char* e = getenv("TCFD_FLOW")) h->flow = h->flow && atoi(e) != 0;
+    if (h->flow) {
+      int W = 64;
+      if (const char* e = getenv("TCFD_FLOW_W")) W = atoi(e) > 0 ? atoi(e) : W;
+      chunk = W < h->max_batch ? W : h->max_batch;
+      if (cudaMalloc(reinterpret_cast<void**>(&h->sync_dev), sizeof(int) * (2 + 2 * (size_t)h->max_batch)) != cudaSuccess ||
+          cudaHostAlloc(reinterpret_cast<void**>(&h->err_host), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+          cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->err_dev), h->err_host, 0) != cudaSuccess)
+        rc = fail(TCFD_ERR_NOMEM, "flow schedule: synchronisation block allocation failed");
+      else
+        *h->err_host = 0;
+    }
     h->chunk = chunk;
     const size_t sb = h->state_bytes(h->chunk);
     // advt: v1 [B][nh][n] complex; v2 [B][n/4+1][n][4 reals] (slightly larger)
@@ -419,6 +492,8 @@ extern "C" int tcfd_ns2d_destroy(tcfd_ns2d_t* h) {
                  h->wS, h->H, h->advt, h->stage_in, h->stage_out, h->stage_dw};
   for (void* p : all)
     if (p) cudaFree(p);
+  if (h->sync_dev) cudaFree(h->sync_dev);
+  if (h->err_host) cudaFreeHost(h->err_host);
   for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -458,6 +533,13 @@ extern "C" int tcfd_ns2d_set_forcing(tcfd_ns2d_t* h, const void* f_hat) {
   return TCFD_OK;
 }
 
+extern "C" int tcfd_ns2d_check(const tcfd_ns2d_t* h) {
+  if (!h) return fail(TCFD_ERR_INVALID, "null handle");
+  if (h->err_host && *reinterpret_cast<volatile int*>(h->err_host) != 0)
+    return fail(TCFD_ERR_CUDA, "dataflow schedule: a dependency wait timed out in an earlier call; results are invalid");
+  return TCFD_OK;
+}
+
 extern "C" size_t tcfd_ns2d_workspace_bytes(const tcfd_ns2d_t* h) { return h ? h->ws_bytes : 0; }
 extern "C" int tcfd_ns2d_last_launch_count(const tcfd_ns2d_t* h) { return h ? h->launches : 0; }
 
@@ -470,6 +552,15 @@ extern "C" int tcfd_ns2d_step(tcfd_ns2d_t* h, const void* w_in, void* w_out, voi
   if (w_in == w_out) return fail(TCFD_ERR_INVALID, "w_out must not alias w_in");
   if (steps < 1 || nstages < 1) return fail(TCFD_ERR_INVALID, "steps and nstages must be >= 1");
   h->launches = 0;
+  if ((rc = tcfd_ns2d_check(h))) return rc;
+  if (h->flow && nstages <= tcfd::FLOW_MAX_STAGES) {
+    const int nd = h->n / 4 + 1, nq = h->n / 4;
+    const double items = (double)batch * ((double)nd + (double)steps * nstages * (nd + nq));
+    if (items < 1.0e9)
+      return h->prec == 32
+                 ? flow_step_impl<float>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream)
+                 : flow_step_impl<double>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream);
+  }
   return h->prec == 32
              ? step_impl<float>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream)
              : step_impl<double>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream);

@@ -1,0 +1,537 @@
+// Third-generation schedule of hot path A for N >= 256: ONE persistent launch per call.
+//
+// The second-generation kernels (ns2d_v2.cuh) run a substage as two grid-wide launches, so the
+// intermediate fields H (4 spectra-sized arrays per sample) and advt make a round trip through HBM:
+// 835 MB of DRAM traffic per substage at 512^2 x 64 against 242 MB of algorithmic state traffic.
+// Here the same unit bodies (rows item = one double row pair of one sample, cols item = one quad of
+// physical columns of one sample) are work items of a single persistent kernel:
+//
+//   * items are handed out in a fixed order by a global ticket counter; the order is CHUNK-MAJOR:
+//     for each chunk of W samples -> [prologue rows] -> { [cols], [rows] } x (steps x stages), each
+//     phase sample-major, so a chunk's state, H and advt (W slots each, re-used by the next chunk:
+//     the lines are overwritten in L2 before they are ever evicted dirty) live in the 126 MB L2 from
+//     the first to the last substage of the call;
+//   * the dependencies (a cols item needs every rows unit of its sample and substage, a rows unit
+//     every cols quad of the previous phase) are per-sample counters in global memory: producers
+//     add 1 with release semantics, the consumer's thread 0 polls with acquire semantics.  An item
+//     only ever waits for items with SMALLER tickets, which are already held by resident CTAs, so
+//     the schedule cannot deadlock whatever the number of resident CTAs is (the polling loop is
+//     nevertheless bounded by the SM clock and reports through an error word instead of hanging);
+//   * the next ticket is fetched while the current item is processed;
+//   * an item is a GROUP of consecutive units of one sample (GR double rows / GC column quads): one
+//     ticket, one dependency poll and one release per group, and inside the group the inputs of unit
+//     g+1 (state, tables, advection row, H tile) are staged by the TMA engine while unit g is being
+//     transformed.
+//
+// Arithmetic, layouts of H / advt / the unit-layout state and the table blocks: ns2d_v2.cuh.
+#pragma once
+#include "ns2d_v2.cuh"
+
+namespace tcfd {
+
+constexpr int FLOW_MAX_STAGES = 8;
+
+template <class T>
+struct FlowParams {
+  NsParams<T> p;  // p.B = samples of this call; workspaces hold `slots` samples
+  int nsub;       // substages of the call = steps * nstages
+  int nstages;
+  int W;          // samples per chunk (== slots of H / advt / wU / hU)
+  T beta[FLOW_MAX_STAGES], gdt[FLOW_MAX_STAGES], mu[FLOW_MAX_STAGES];
+  unsigned char rd_h[FLOW_MAX_STAGES], wr_h[FLOW_MAX_STAGES];
+  cx<typename pack2<T>::type>* wU;  // [W] unit-layout state, updated in place
+  cx<typename pack2<T>::type>* hU;  // [W]
+  cx<typename pack2<T>::type>* w0U; // [W] unit-layout copy of the call's input state (dw/dt), or null
+  int* sync;  // [0] ticket, [1] unused, [2 .. 2+B) rows counters, [2+B .. 2+2B) cols counters
+  int* err;   // host-visible error word (0 = ok)
+};
+
+// ------------------------------------------------------------------------------------------ sync
+TCFD_D int flow_fetch_add(int* p, int v) {
+#ifndef TCFD_EMU
+  return atomicAdd(p, v);
+#else
+  const int o = *p;
+  *p = o + v;
+  return o;
+#endif
+}
+TCFD_D int flow_ld_acquire(const int* p) {
+#ifndef TCFD_EMU
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return *p;
+#endif
+}
+// one thread, after a CTA barrier that follows the item's global stores
+TCFD_D void flow_signal(int* p) {
+#ifndef TCFD_EMU
+  // release at gpu scope: cumulative over the stores of the whole CTA (ordered before by bar.sync)
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+#else
+  *p += 1;
+#endif
+}
+// one thread: wait until *p >= target.  A wait that exceeds ~3 s of SM clock is a lost dependency
+// (never a legitimate wait): the error word is raised and the grid is killed instead of hanging.
+TCFD_D void flow_wait(const int* p, int target, int* err) {
+#ifndef TCFD_EMU
+  if (flow_ld_acquire(p) < target) {
+    const long long t0 = clock64();
+    unsigned ns = 32;
+    for (unsigned spin = 1;; ++spin) {
+      __nanosleep(ns);
+      if (ns < 1024) ns *= 2;  // back off: hundreds of CTAs polling one word would starve the producers' REDs
+      if (flow_ld_acquire(p) >= target) break;
+      if ((spin & 255u) == 0 && (*reinterpret_cast<volatile int*>(err) != 0 || clock64() - t0 > 6000000000ll)) {
+        *reinterpret_cast<volatile int*>(err) = 1;
+        __threadfence_system();
+        asm volatile("trap;");
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");  // bulk / TMA reads of the producer's stores follow
+#else
+  if (*p < target) {  // sequential emulation: a dependency with a larger ticket is a schedule bug
+    *err = 1;
+    std::abort();
+  }
+#endif
+}
+template <class V>
+TCFD_D V flow_ld_cg(const V* p) {  // L2-only load: the line may have been rewritten by another SM
+#ifndef TCFD_EMU
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+#ifndef TCFD_EMU
+TCFD_D cx<f2> flow_ld_cg(const cx<f2>* p) {
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+  return cx<f2>{f2(v.x, v.y), f2(v.z, v.w)};
+}
+TCFD_D cx<d2> flow_ld_cg(const cx<d2>* p) {
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  return cx<d2>{d2(a.x, a.y), d2(b.x, b.y)};
+}
+#endif
+
+// ------------------------------------------------------------------------------------------ smem
+// One layout for both roles:
+//   cols: [ tile ]                                              [ buf ] [ barriers ]
+//   rows: [ W | H | ADV (advection row / dw/dt reference) | TAB0 | MASK0 | TAB1 | MASK1 ]
+template <class T, int N>
+struct FlowSmem {
+  typedef typename pack2<T>::type L;
+  typedef RowsSmem<T, N> R;
+  static constexpr int NH = N / 2 + 1;
+  static constexpr int IB = 4 * (int)sizeof(cx<L>);
+  typedef TileGeom<NH, IB> G;
+  static constexpr int TABM = R::TAB_BYTES + 2 * R::MASK_ROW;  // one table block + its mask rows
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_H = R::UNIT_BYTES;
+  static constexpr int OFF_ADV = 2 * R::UNIT_BYTES;  // UNIT_BYTES >= N entries
+  static constexpr int OFF_TAB = 3 * R::UNIT_BYTES;
+  static constexpr int ROWS_STAGE = OFF_TAB + 2 * TABM;
+  static constexpr int AREA = (G::BYTES > ROWS_STAGE ? G::BYTES : ROWS_STAGE);
+  static constexpr int OFF_BUF = (AREA + 127) / 128 * 128;
+  static constexpr int OFF_BAR = OFF_BUF + N * (int)sizeof(cx<L>);
+  static constexpr int BYTES = OFF_BAR + 64 + 1024;  // + slack for the 1 KB alignment of the area
+};
+
+// Two of the four spectra at one entry (lanes (psi-derived, w-derived)); a = half ? -kx : ky,
+// b = half ? ky : kx  (bitwise the same values as ns_fields_s<HALF>)
+template <class T>
+TCFD_D cx<typename pack2<T>::type> ns_fields_rt(cx<T> w, T nil, T a, T b) {
+  typedef typename pack2<T>::type L;
+  const T px = nil * w.x, py = nil * w.y;  // psi
+  return cx<L>{L(-(a * py), -(b * w.y)), L(a * px, b * w.x)};
+}
+template <class L>
+TCFD_D cx<typename lane_traits<L>::scalar> lane_rt(cx<L> v, int lane) {
+  typedef typename lane_traits<L>::scalar T;
+  return lane ? cx<T>{v.x.hi, v.y.hi} : cx<T>{v.x.lo, v.y.lo};
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+// GR: double rows per rows item, GC: column quads per cols item (GC divides N/4).
+template <class T, int N, int MINB, int GR, int GC>
+__global__ void __launch_bounds__(N / 8, MINB)
+ns2d_flow_kernel(const FlowParams<T> fp, const
+#ifndef TCFD_EMU
+                 __grid_constant__
+#endif
+                 TileMaps maps) {
+  typedef typename pack2<T>::type L;
+  typedef FlowSmem<T, N> S;
+  typedef typename S::G G;
+  typedef typename S::R R;
+  constexpr int NT = N / 8, NH = N / 2 + 1, ND = N / 4 + 1, NQ = N / 4;
+  constexpr int IR = (ND + GR - 1) / GR;  // rows items per sample and phase
+  constexpr int IC = NQ / GC;             // cols items per sample and phase
+  static_assert(NQ % GC == 0, "GC must divide N/4");
+  constexpr int IB = S::IB;
+  const NsParams<T>& p = fp.p;
+  TCFD_DYN_SMEM(smem_raw);
+  unsigned char* area = smem_raw + ((1024u - (smem_offset(smem_raw) & 1023u)) & 1023u);
+  unsigned char* tile = area;
+  cx<L>* buf = reinterpret_cast<cx<L>*>(area + S::OFF_BUF);
+  const cx<L>* wst = reinterpret_cast<const cx<L>*>(area + S::OFF_W);
+  const cx<L>* hst = reinterpret_cast<const cx<L>*>(area + S::OFF_H);
+  const cx<L>* advst = reinterpret_cast<const cx<L>*>(area + S::OFF_ADV);
+  unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(area + S::OFF_BAR);  // state / tile
+  unsigned long long* bar_t = bar_s + 1;                                                  // tables
+  unsigned long long* bar_a = bar_s + 2;                                                  // advection row
+  unsigned long long* bar_o = bar_s + 3;                                                  // dw/dt reference
+  volatile int* sh = reinterpret_cast<volatile int*>(bar_s + 4);                          // [0] ticket
+
+  const int t = threadIdx.x;
+  FftTwiddles<T, N> tw;
+  tw.load(p.tw, t);
+  CtaSync sync;
+  int parity = 0;
+  T kyv[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) kyv[m] = p.kappa_y[m < 4 ? t + m * NT : N - t - m * NT];
+
+  int* ticket = fp.sync;
+  int* cnt_rows = fp.sync + 2;
+  int* cnt_cols = fp.sync + 2 + p.B;
+  const int W = fp.W;
+  const int nsub = fp.nsub;
+  constexpr int per_pair = IR + IC;  // items of one {cols, rows} pair per sample
+  const int nchunks = (p.B + W - 1) / W;
+  const long long per_chunk = (long long)W * (IR + (long long)nsub * per_pair);  // items of a full chunk
+  const bool want_dwdt = p.dwdt != nullptr;
+
+  int next_tk = 0;  // thread 0: the ticket of the next item (requested one item ahead)
+  if (t == 0) {
+    stage_barrier_init(bar_s);
+    stage_barrier_init(bar_t);
+    stage_barrier_init(bar_a);
+    stage_barrier_init(bar_o);
+#ifndef TCFD_EMU
+    tma_prefetch_desc(&maps.main);
+    tma_prefetch_desc(&maps.last);
+#endif
+    next_tk = flow_fetch_add(ticket, 1);
+    sh[0] = next_tk;
+  }
+  int it = 0;  // items processed by this CTA: the ticket mailbox alternates between sh[0] and sh[1]
+  unsigned phase_s = 0, phase_t = 0, phase_a = 0, phase_o = 0;
+  int* pending = nullptr;  // thread 0: counter of the item whose stores were just fenced by the barrier
+  __syncthreads();
+
+  for (;;) {
+    // here: the previous item is complete (its stores are ordered before the last barrier, shared
+    // memory is free) and sh[0] holds this item's ticket
+    const int tk = sh[it & 1];
+    ++it;
+    if (t == 0) {
+      if (pending) flow_signal(pending);
+      pending = nullptr;
+      next_tk = flow_fetch_add(ticket, 1);  // consumed at the end of this item
+    }
+    // ---- decode (chunks are equal-sized except the last)
+    const int c = (int)((long long)tk / per_chunk);
+    if (c >= nchunks) break;
+    const int Wc = (c == nchunks - 1) ? p.B - c * W : W;
+    int r = (int)((long long)tk - (long long)c * per_chunk);
+    if (r >= Wc * (IR + nsub * per_pair)) break;  // past the end (last chunk)
+    bool is_rows;
+    int j, u;  // substage (-1 = prologue), item index inside the phase
+    if (r < Wc * IR) {
+      is_rows = true; j = -1; u = r;
+    } else {
+      r -= Wc * IR;
+      j = r / (Wc * per_pair);
+      const int q = r % (Wc * per_pair);
+      is_rows = q >= Wc * IC;
+      u = is_rows ? q - Wc * IC : q;
+    }
+
+    if (!is_rows) {
+      // ================================================================= cols item: GC quads
+      const int sl = u / IC, q0 = (u % IC) * GC;  // slot inside the chunk, first quad
+      const int s = c * W + sl;
+      if (t == 0) {
+        flow_wait(&cnt_rows[s], IR * (j + 1), fp.err);
+        tile_load_issue<NH, IB>(tile, maps, q0 * 4, sl, bar_s);
+      }
+#pragma unroll 1
+      for (int g = 0; g < GC; ++g) {
+        const int y0 = (q0 + g) * 4;
+        cx<L> cc[1][8];
+        tile_load_wait(bar_s, phase_s);
+        phase_s ^= 1u;
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+          cx<L> z[1][8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int k = t + m * NT;
+            const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
+            const int row = lo ? k : N - k;
+            const cx<L> A = tile_ld<T, G>(tile, row, 0, cidx);
+            const cx<L> Bv = tile_ld<T, G>(tile, row, 1, cidx);
+            z[0][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
+            if ((m == 0 || m == 4) && t == 0) z[0][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
+          }
+          fft_run<L, N, +1, 1, false, N>(z, tw, buf, parity, t, sync);
+          if (cidx == 3) {
+            // every thread has passed a barrier after its last tile read: the tile is free
+            if (t == 0 && g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
+          }
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const T adv = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
+            if (cidx == 0) cc[0][m].x.lo = adv;
+            if (cidx == 1) cc[0][m].y.lo = adv;
+            if (cidx == 2) cc[0][m].x.hi = adv;
+            if (cidx == 3) cc[0][m].y.hi = adv;
+          }
+        }
+        fft_run<L, N, -1, 1, false, N>(cc, tw, buf, parity, t, sync);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) buf[t + m * NT] = cc[0][m];
+        __syncthreads();
+        cx<L>* dst = reinterpret_cast<cx<L>*>(p.advt2) + (size_t)sl * ND * N + y0;
+        for (int jj = t; jj < p.NDF; jj += NT) {
+          const int k = 2 * jj;
+          const cx<L> c0 = buf[k], c1 = buf[k + 1], n0 = buf[(N - k) % N], n1 = buf[N - k - 1];
+          const L hf(T(0.5));
+          const L Ea = hf * (c0.x + n0.x), Fa = hf * (c0.y - n0.y), Ga = hf * (c0.y + n0.y), Ha = hf * (n0.x - c0.x);
+          const L Eb = hf * (c1.x + n1.x), Fb = hf * (c1.y - n1.y), Gb = hf * (c1.y + n1.y), Hb = hf * (n1.x - c1.x);
+          cx<L>* o = dst + (size_t)jj * N;
+          o[0] = cx<L>{L(Ea.lo, Eb.lo), L(Fa.lo, Fb.lo)};
+          o[1] = cx<L>{L(Ga.lo, Gb.lo), L(Ha.lo, Hb.lo)};
+          o[2] = cx<L>{L(Ea.hi, Eb.hi), L(Fa.hi, Fb.hi)};
+          o[3] = cx<L>{L(Ga.hi, Gb.hi), L(Ha.hi, Hb.hi)};
+        }
+        if (g + 1 < GC) __syncthreads();  // buf is re-used by the next quad's transforms
+      }
+      if (t == 0) {
+        sh[it & 1] = next_tk;
+        pending = &cnt_cols[s];
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // =================================================================== rows item: up to GR units
+    const int sl = u / IR, d0 = (u % IR) * GR;
+    const int gn = (ND - d0) < GR ? (ND - d0) : GR;
+    const int s = c * W + sl;
+    const bool prologue = j < 0;
+    const int k = prologue ? 0 : j % fp.nstages;
+    const bool last_sub = (j == nsub - 1);
+    const bool do_inv = !last_sub;
+    const bool rd_h = !prologue && fp.rd_h[k], wr_h = !prologue && fp.wr_h[k];
+    const bool ld_old = last_sub && want_dwdt;  // dw/dt needs the call's input state
+    const size_t sb = (size_t)s * N * NH;  // reference layout: sample base
+    const T beta = fp.beta[k], gdt = fp.gdt[k], mu = fp.mu[k];
+
+    // one thread: stage the inputs of unit d (unit index g inside the item) -- tables always, state and
+    // advection row for substage items
+    auto issue_unit = [&](int d, int g) {
+      unsigned char* tabdst = area + S::OFF_TAB + (g & 1) * S::TABM;
+      stage_expect(bar_t, (unsigned)S::TABM);
+      bulk_load(tabdst, reinterpret_cast<const unsigned char*>(p.tabU) + (size_t)d * R::TAB_BYTES, (unsigned)R::TAB_BYTES, bar_t);
+      bulk_load(tabdst + R::TAB_BYTES, p.maskU + (size_t)d * 2 * R::MASK_ROW, (unsigned)(2 * R::MASK_ROW), bar_t);
+      if (!prologue) {
+        const size_t ub = ((size_t)sl * ND + d) * 2 * NH;
+        stage_expect(bar_s, (unsigned)R::UNIT_BYTES * (1u + (rd_h ? 1u : 0u)));
+        bulk_load(area + S::OFF_W, fp.wU + ub, (unsigned)R::UNIT_BYTES, bar_s);
+        if (rd_h) bulk_load(area + S::OFF_H, fp.hU + ub, (unsigned)R::UNIT_BYTES, bar_s);
+        if (d < p.NDF) {
+          stage_expect(bar_a, (unsigned)(N * sizeof(cx<L>)));
+          bulk_load(area + S::OFF_ADV, reinterpret_cast<const cx<L>*>(p.advt2) + ((size_t)sl * ND + d) * N,
+                    (unsigned)(N * sizeof(cx<L>)), bar_a);
+        }
+      }
+    };
+    if (t == 0) {
+      if (prologue) {
+        if (s >= W) flow_wait(&cnt_rows[s - W], IR * (nsub + 1), fp.err);
+      } else {
+        flow_wait(&cnt_cols[s], IC * (j + 1), fp.err);
+      }
+      issue_unit(d0, 0);
+    }
+
+#pragma unroll 1
+    for (int g = 0; g < gn; ++g) {
+      const int d = d0 + g;
+      const size_t ub = ((size_t)sl * ND + d) * 2 * NH;  // unit layout: block base (slot)
+      const bool valid1 = 2 * d + 1 <= N / 2;
+      const int r1a = 2 * d, r2a = (N - r1a) % N;
+      const int r1b = valid1 ? 2 * d + 1 : r1a, r2b = (N - r1b) % N;
+      const bool selfa = r1a == r2a, selfb = r1b == r2b;
+      const T kx1a = p.kappa_x[r1a], kx2a = p.kappa_x[r2a], kx1b = p.kappa_x[r1b], kx2b = p.kappa_x[r2b];
+      const unsigned char* tabsrc = area + S::OFF_TAB + (g & 1) * S::TABM;
+      const L* linst = reinterpret_cast<const L*>(tabsrc);
+      const T* nilst = reinterpret_cast<const T*>(tabsrc) + 2 * NH;
+      const unsigned char* maskst = tabsrc + R::TAB_BYTES;
+
+      cx<L> wv[8], e0, e1;  // e0 = entries (r2, 0), e1 = entries (r1, N/2): owned by thread 0
+      if (prologue) {
+        const cx<T>* w = p.w_in + sb;
+        const int lo_a = r1a * NH + t, hi_a = r2a * NH + N - t, lo_b = r1b * NH + t, hi_b = r2b * NH + N - t;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const bool lo = m < 4;
+          const cx<T> w0 = w[lo ? lo_a + m * NT : hi_a - m * NT], w1 = w[lo ? lo_b + m * NT : hi_b - m * NT];
+          wv[m] = cx<L>{L(w0.x, w1.x), L(w0.y, w1.y)};
+        }
+        if (t == 0) {
+          const cx<T> a0 = w[r2a * NH], a1 = w[r2b * NH];
+          e0 = cx<L>{L(a0.x, a1.x), L(a0.y, a1.y)};
+          const cx<T> b0 = w[r1a * NH + N / 2], b1 = w[r1b * NH + N / 2];
+          e1 = cx<L>{L(b0.x, b1.x), L(b0.y, b1.y)};
+        }
+        // the table block was issued by thread 0 AFTER its dependency wait: its arrival also tells
+        // every other thread that the slot's previous occupant is done (stores below re-use the slot)
+        tile_load_wait(bar_t, phase_t);
+        phase_t ^= 1u;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const size_t o = ub + (m < 4 ? 0 : NH) + (m < 4 ? t + m * NT : N - t - m * NT);
+          fp.wU[o] = wv[m];
+          if (want_dwdt) fp.w0U[o] = wv[m];
+        }
+        if (t == 0) {
+          fp.wU[ub + NH + 0] = e0;
+          fp.wU[ub + N / 2] = e1;
+          if (want_dwdt) {
+            fp.w0U[ub + NH + 0] = e0;
+            fp.w0U[ub + N / 2] = e1;
+          }
+        }
+      } else {
+        const bool forced = p.fhat && (p.frow[r1a] | p.frow[r2a] | p.frow[r1b] | p.frow[r2b]);
+        cx<L> a[1][8];
+        if (d < p.NDF) {
+          tile_load_wait(bar_a, phase_a);
+          phase_a ^= 1u;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) a[0][m] = advst[t + m * NT];
+          fft_run<L, N, -1, 1, false, N>(a, tw, buf, parity, t, sync);
+        } else {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) a[0][m] = cx<L>{L(T(0)), L(T(0))};
+          if (ld_old) __syncthreads();  // the ADV stage was last read by the previous unit's update
+        }
+        if (ld_old) {
+          // the advection row is in registers (a barrier of the transform lies behind its reads): the
+          // ADV stage takes this unit's block of the call's input state
+          if (t == 0) {
+            stage_expect(bar_o, (unsigned)R::UNIT_BYTES);
+            bulk_load(area + S::OFF_ADV, fp.w0U + ub, (unsigned)R::UNIT_BYTES, bar_o);
+          }
+        }
+        tile_load_wait(bar_t, phase_t);
+        phase_t ^= 1u;
+        tile_load_wait(bar_s, phase_s);
+        phase_s ^= 1u;
+        if (ld_old) {
+          tile_load_wait(bar_o, phase_o);
+          phase_o ^= 1u;
+        }
+        // RK / CN update of entry (half, col) in both lanes; returns the new w
+        auto update = [&](int half, int col, cx<L> A, bool own_a, bool own_b) -> cx<L> {
+          const int ra = half ? r2a : r1a, rb = half ? r2b : r1b;
+          const L lin = linst[col];
+          const unsigned mk = maskst[half * R::MASK_ROW + col];
+          const L f((mk & 1u) ? T(1) : T(0), (mk & 2u) ? T(1) : T(0));
+          cx<L> F{f * A.x, f * A.y};
+          if (forced) {
+            const cx<T> f0 = p.fhat[ra * NH + col], f1 = p.fhat[rb * NH + col];
+            F = F + cx<L>{L(f0.x, f1.x), L(f0.y, f1.y)};
+          }
+          const cx<L> w = wst[half * NH + col];
+          cx<L> h = F;
+          if (rd_h) h = F + L(beta) * hst[half * NH + col];
+          if (wr_h) fp.hU[ub + half * NH + col] = h;
+          const L den = L(T(1)) - L(mu) * lin;
+          const L inv(rcp_rn(den.lo), rcp_rn(den.hi));
+          const cx<L> x = (w + L(gdt) * h) + L(mu) * (lin * w);
+          const cx<L> wn = inv * x;
+          if (last_sub) {
+            if (own_a) p.w_out[sb + ra * NH + col] = cx<T>{wn.x.lo, wn.y.lo};
+            if (own_b) p.w_out[sb + rb * NH + col] = cx<T>{wn.x.hi, wn.y.hi};
+            if (want_dwdt) {
+              const cx<L> o = advst[half * NH + col];
+              if (own_a) p.dwdt[sb + ra * NH + col] = cx<T>{p.inv_tdt * (wn.x.lo - o.x.lo), p.inv_tdt * (wn.y.lo - o.y.lo)};
+              if (own_b) p.dwdt[sb + rb * NH + col] = cx<T>{p.inv_tdt * (wn.x.hi - o.x.hi), p.inv_tdt * (wn.y.hi - o.y.hi)};
+            }
+          } else {
+            fp.wU[ub + half * NH + col] = wn;
+          }
+          return wn;
+        };
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const bool lo = m < 4;
+          const int col = lo ? t + m * NT : N - t - m * NT;
+          const bool first = lo || (m == 4 && t == 0);
+          wv[m] = update(lo ? 0 : 1, col, lo ? a[0][m] : conj(a[0][m]), first || !selfa, valid1 && (first || !selfb));
+        }
+        if (t == 0) {
+          e0 = update(1, 0, conj(a[0][0]), !selfa, valid1 && !selfb);
+          e1 = update(0, N / 2, a[0][4], !selfa, valid1 && !selfb);
+        }
+      }
+      // the W / H / ADV stages are consumed (and the other table block has been free since the
+      // previous unit's inverse transforms): stage the next unit under this unit's inverse transforms
+      if (g + 1 < gn) {
+        __syncthreads();
+        if (t == 0) issue_unit(d + 1, g + 1);
+      }
+
+      if (do_inv) {
+        const int nq = valid1 ? 4 : 2;
+        const T ky0 = p.kappa_y[0], kyh = p.kappa_y[N / 2];
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
+          const int lane = q >> 1, half = q & 1;
+          const T kx1 = lane ? kx1b : kx1a, kx2 = lane ? kx2b : kx2a;
+          const int r1 = lane ? r1b : r1a;
+          const T* nl = nilst + lane * NH;
+          cx<L> z[1][8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const bool lo = m < 4;
+            const T kx = lo ? kx1 : kx2;
+            const T nil = nl[lo ? t + m * NT : N - t - m * NT];
+            const cx<L> f = ns_fields_rt<T>(lane_rt(wv[m], lane), nil, half ? -kx : kyv[m], half ? kyv[m] : kx);
+            z[0][m] = lo ? f : conj(f);
+          }
+          if (t == 0) {
+            // self-conjugate columns ky = 0 and ky = N/2: Hermitian part of the two rows (C2R semantics)
+            const T n0 = nl[0], nh = nl[N / 2];
+            const cx<L> f1 = ns_fields_rt<T>(lane_rt(wv[0], lane), n0, half ? -kx1 : ky0, half ? ky0 : kx1);
+            const cx<L> f2_ = ns_fields_rt<T>(lane_rt(e0, lane), n0, half ? -kx2 : ky0, half ? ky0 : kx2);
+            const cx<L> g1 = ns_fields_rt<T>(lane_rt(e1, lane), nh, half ? -kx1 : kyh, half ? kyh : kx1);
+            const cx<L> g2 = ns_fields_rt<T>(lane_rt(wv[4], lane), nh, half ? -kx2 : kyh, half ? kyh : kx2);
+            z[0][0] = L(T(0.5)) * (f1 + conj(f2_));
+            z[0][4] = L(T(0.5)) * (g1 + conj(g2));
+          }
+          fft_run<L, N, +1, 1, false, N>(z, tw, buf, parity, t, sync);
+          cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + (size_t)half * p.Hplane + ((size_t)sl * NH + r1) * (size_t)N + t;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) Hrow[m * NT] = z[0][m];
+        }
+      }
+    }
+    if (t == 0) {
+      sh[it & 1] = next_tk;
+      pending = &cnt_rows[s];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace tcfd

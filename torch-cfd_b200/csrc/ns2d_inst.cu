@@ -1,8 +1,10 @@
 // One translation unit per (precision, N): compiled with -DTCFD_PREC=32|64 -DTCFD_N=<n>.
 // Exports a C launcher table entry used by ns2d_api.cu.  N >= 256 gets the second-generation
 // kernels (ns2d_v2.cuh), smaller grids the CTA-tiled ones (ns2d_kernels.cuh).
-#include "ns2d_v2.cuh"
+#include "ns2d_flow.cuh"
 #include "ns2d_plan.h"
+#include <cstdio>
+#include <cstdlib>
 
 #if TCFD_PREC == 32
 typedef float real_t;
@@ -171,6 +173,53 @@ int launch(int which, const NsParams<real_t>& p, const TileMaps* maps, int num_s
   }
   return 0;
 }
+
+#ifndef TCFD_FLOW_MINB
+#define TCFD_FLOW_MINB MINB_BY_THREADS
+#endif
+constexpr size_t FLOW_SMEM = (size_t)FlowSmem<real_t, N>::BYTES;
+constexpr int FLOW_BY_SMEM = (int)(232448 / (FLOW_SMEM + 1024));
+constexpr int FLOW_MINB = FLOW_BY_SMEM < 1 ? 1 : (FLOW_BY_SMEM < TCFD_FLOW_MINB ? FLOW_BY_SMEM : TCFD_FLOW_MINB);
+
+template <int GR, int GC, int MAXR>
+int launch_flow_g(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms, cudaStream_t stream) {
+  static int occ = 0;
+  auto k = ns2d_flow_kernel<real_t, N, FLOW_MINB, GR, GC>;
+  int rc = 0;
+  if (!occ && (rc = prep(k, FLOW_SMEM, NT, &occ))) return rc;
+#ifdef TCFD_EMU
+  const int grid = 2;
+#else
+  const int grid = num_sms * occ;
+#endif
+  TCFD_LAUNCH(k, grid, NT, FLOW_SMEM, stream, fp, *maps);
+  return 0;
+}
+
+// group sizes (double rows per rows item, column quads per cols item) and register cap (0: from
+// __launch_bounds__); TCFD_FLOW_G="<GR>,<GC>,<MAXR>" selects one of the other compiled variants
+// (schedule experiments, -DTCFD_FLOW_VARIANTS builds only)
+int launch_flow(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms, cudaStream_t stream) {
+  if (!maps) return -2;
+  static int gr = 0, gc = 0, mr = 0;
+  if (!gr) {
+    gr = 1;
+    gc = 1;
+    if (const char* e = getenv("TCFD_FLOW_G")) {
+      int a = 0, b = 0, c = 0;
+      const int nf = sscanf(e, "%d,%d,%d", &a, &b, &c);
+      if (nf >= 2) { gr = a; gc = b; mr = nf == 3 ? c : 0; }
+    }
+  }
+#define TCFD_FLOW_CASE(A, B, C) if (gr == A && gc == B && mr == C) return launch_flow_g<A, B, C>(fp, maps, num_sms, stream);
+  TCFD_FLOW_CASE(1, 1, 0)
+#ifdef TCFD_FLOW_VARIANTS
+  TCFD_FLOW_CASE(3, 4, 0)
+  TCFD_FLOW_CASE(2, 2, 0)
+#endif
+#undef TCFD_FLOW_CASE
+  return -3;
+}
 }  // namespace v2
 #endif
 
@@ -191,6 +240,19 @@ int launch(int which, const void* params, const void* maps, int num_sms, void* s
   return 0;
 #endif
 }
+
+#if TCFD_N >= 256
+int launch_flow(const void* params, const void* maps, int num_sms, void* stream_) {
+  int rc = v2::launch_flow(*static_cast<const FlowParams<real_t>*>(params), static_cast<const TileMaps*>(maps), num_sms,
+                           static_cast<cudaStream_t>(stream_));
+  if (rc) return rc;
+#ifndef TCFD_EMU
+  return (int)cudaGetLastError();
+#else
+  return 0;
+#endif
+}
+#endif
 }  // namespace
 
 #define TCFD_CAT3(a, b, c) a##b##_##c
@@ -205,4 +267,11 @@ extern "C" void TCFD_ENTRY(TCFD_PREC, TCFD_N)(tcfd_ns2d_entry_t* e) {
 #endif
   e->v2 = V2 ? 1 : 0;
   e->launch = &launch;
+#if TCFD_N >= 256
+  e->flow_ctas_per_sm = (int)(232448 / ((size_t)FlowSmem<real_t, N>::BYTES + 1024));
+  e->launch_flow = e->flow_ctas_per_sm > 0 ? &launch_flow : nullptr;
+#else
+  e->flow_ctas_per_sm = 0;
+  e->launch_flow = nullptr;
+#endif
 }

@@ -7,4 +7,8 @@ typedef struct {
   int v2;  // 1: ns2d_v2.cuh kernels (packed layouts H2/advt2, TMA tile maps), 0: ns2d_kernels.cuh
   // maps: const tcfd::TileMaps* (v2 cols kernel only, may be null otherwise)
   int (*launch)(int which, const void* params, const void* maps, int num_sms, void* stream);
+  // third-generation persistent dataflow kernel (ns2d_flow.cuh): params = const tcfd::FlowParams<T>*;
+  // null when the size has no such kernel
+  int (*launch_flow)(const void* flow_params, const void* maps, int num_sms, void* stream);
+  int flow_ctas_per_sm;  // CTAs per SM the flow kernel's shared memory allows (0: does not fit)
 } tcfd_ns2d_entry_t;
