@@ -213,8 +213,29 @@ def run_ours(a):
     assert torch.isfinite(torch.view_as_real(w)).all().item(), "state blew up"
     value = world * K / (ms * 1e-3)
 
-    # ---------------- per-kernel device times (separate instrumented pass, same workload)
-    kt = plan.kernel_times(w, DT, ns.solver, steps=3)
+    # ---------------- per-kernel device times (separate instrumented pass, same workload): every
+    # launch bracketed by CUDA events on the launching stream (tcfd_ns2d_step_timed).  Under the
+    # dataflow schedule a call is ONE launch, so single-step calls are timed (the bench's own call shape).
+    flow = plan.dataflow
+    if flow:
+        acc = None
+        reps = 10
+        for _ in range(reps):
+            k1 = plan.kernel_times(w, DT, ns.solver, steps=1)
+            if acc is None:
+                acc = k1
+            else:
+                for key, v in k1.items():
+                    if isinstance(v, dict):
+                        acc[key]["launches"] += v["launches"]
+                        acc[key]["ms_total"] += v["ms_total"]
+        for v in acc.values():
+            if isinstance(v, dict):
+                v["us_per_launch"] = 1e3 * v["ms_total"] / v["launches"] if v["launches"] else None
+        acc["steps"] = reps
+        kt = acc
+    else:
+        kt = plan.kernel_times(w, DT, ns.solver, steps=3)
 
     # ---------------- end to end: host (pinned) buffers through the public host API
     e2e = None
@@ -244,18 +265,29 @@ def run_ours(a):
     alg_bytes_step = 18 * S * B
     peak, peak_src = peaks()
     achieved = alg_bytes_step * K / (ms * 1e-3) / 1e9  # per GPU
-    # dominant kernel = the substage rows kernel (forward y-FFT + RK/CN update + inverse y-FFTs): it is
-    # the launch that moves the substage's algorithmic bytes (reads w, h; writes w, h: 4 S per sample,
-    # 3 S in the first substage of a step) -- DESIGN.md "Roofline accounting"
-    dom = kt.get("rows_fwd_inv") or {}
-    dom_alg = 3.75 * S * B
+    if flow:
+        # dominant (only) kernel = the persistent dataflow launch of one step: it moves the step's whole
+        # algorithmic traffic, 18 S per sample (DESIGN.md "Roofline accounting")
+        dom_key, dom_name = "flow_call", "ns2d_flow_kernel (one persistent launch = one RK4+CN step of the batch)"
+        dom_alg = 18.0 * S * B
+        dom_note = ("one launch per step: prologue + 5 x (cols, rows) phases as ticketed work items with "
+                    "per-sample dependency counters; H / advt are intermediate traffic, not algorithmic bytes")
+    else:
+        # dominant kernel = the substage rows kernel (forward y-FFT + RK/CN update + inverse y-FFTs): it is
+        # the launch that moves the substage's algorithmic bytes (reads w, h; writes w, h: 4 S per sample,
+        # 3 S in the first substage of a step) -- DESIGN.md "Roofline accounting"
+        dom_key, dom_name = "rows_fwd_inv", "ns2d_rows3_kernel (substage: rows fwd + update + rows inv)"
+        dom_alg = 3.75 * S * B
+        dom_note = ("the cols kernel of the same substage moves no algorithmic bytes (its H/advt traffic is "
+                    "intermediate); the honest whole-step figure is roofline_step")
+    dom = kt.get(dom_key) or {}
     dom_us = dom.get("us_per_launch")
     dom_achieved = dom_alg / (dom_us * 1e-6) / 1e9 if dom_us else None
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if tj["workload"] == {"n": n, "batch": B, "dtype": a.dtype}:
-            traffic = tj["dram_bytes_per_launch"]["rows_fwd_inv"]
+            traffic = tj["dram_bytes_per_launch"][dom_key]
     except (OSError, KeyError, ValueError):
         pass
     step_us = sum(v["ms_total"] for v in kt.values() if isinstance(v, dict)) * 1e3 / kt["steps"]
@@ -269,15 +301,15 @@ def run_ours(a):
         "config": {"workload": f"Kolmogorov-forced 2D vorticity RK4+CN, {n}x{n}, batch {B} per GPU, {a.dtype}",
                    "global_batch": B * world, "viscosity": VISC, "drag": DRAG, "dt": DT,
                    "l2": f"working set (state w+h {2 * S * B / 1e6:.0f} MB + workspace) exceeds the 126 MB L2; no flush",
+                   "schedule": "dataflow (1 launch per call)" if flow else "two launches per substage",
                    "sample_steps_per_s": value * B, "cell_steps_per_s": value * B * n * n},
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
-        "roofline": {"bound": "hbm", "kernel": "ns2d_rows3_kernel (substage: rows fwd + update + rows inv)",
+        "roofline": {"bound": "hbm", "kernel": dom_name,
                      "achieved": dom_achieved, "peak": peak, "unit": "GB/s",
                      "frac": dom_achieved / peak if dom_achieved else None, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_alg,
                      "us_per_launch": dom_us, "share_of_step": (dom["ms_total"] * 1e3 / kt["steps"]) / step_us if dom_us else None,
-                     "note": "the cols kernel of the same substage moves no algorithmic bytes (its H/advt "
-                             "traffic is intermediate); the honest whole-step figure is roofline_step"},
+                     "note": dom_note},
         "roofline_step": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                           "algorithmic_bytes_per_step": alg_bytes_step,
                           "note": "18 S B bytes per step over the device time of ALL launches of the step"},

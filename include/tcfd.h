@@ -70,6 +70,9 @@ size_t tcfd_ns2d_workspace_bytes(const tcfd_ns2d_t* h);
  * failure through the handle's host-visible error word; meaningful after the stream was synchronised.
  * Every tcfd_ns2d_step call performs this check on entry. */
 int tcfd_ns2d_check(const tcfd_ns2d_t* h);
+/* launch schedule of tcfd_ns2d_step on this handle: 1 = one persistent dataflow launch per call
+ * (n >= 256; environment TCFD_FLOW=0 at creation selects the other), 0 = two launches per substage */
+int tcfd_ns2d_schedule(const tcfd_ns2d_t* h);
 /* number of kernel launches the last tcfd_ns2d_* compute call enqueued */
 int tcfd_ns2d_last_launch_count(const tcfd_ns2d_t* h);
 
@@ -89,7 +92,8 @@ int tcfd_ns2d_step(tcfd_ns2d_t* h, const void* w_in, void* w_out, void* dwdt, in
 /* Measurement twin of tcfd_ns2d_step (no reference counterpart): brackets EVERY kernel launch of
  * the step with CUDA events on `stream`, synchronises the stream, and returns the summed device
  * time ms[4] and launch count count[4] per kernel kind (0 = rows-inverse prologue, 1 = rows
- * forward+inverse, 2 = rows forward epilogue, 3 = cols).  Used by bench.py for the roofline. */
+ * forward+inverse -- or, under the dataflow schedule, the single persistent launch of the call --
+ * 2 = rows forward epilogue, 3 = cols).  Used by bench.py for the roofline. */
 int tcfd_ns2d_step_timed(tcfd_ns2d_t* h, const void* w_in, void* w_out, int batch, int steps, int nstages,
                          const double* beta, const double* gdt, const double* mu, void* stream, float* ms,
                          int* count);

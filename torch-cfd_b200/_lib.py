@@ -59,6 +59,8 @@ class TcfdLibrary:
         c.tcfd_ns2d_workspace_bytes.restype = ctypes.c_size_t
         c.tcfd_ns2d_last_launch_count.argtypes = [vp]
         c.tcfd_ns2d_check.argtypes = [vp]
+        c.tcfd_ns2d_schedule.argtypes = [vp]
+        c.tcfd_ns2d_schedule.restype = ctypes.c_int
         c.tcfd_ns2d_check.restype = ctypes.c_int
         c.tcfd_ns2d_step.argtypes = [vp, vp, vp, vp, ci, ci, ci, dp, dp, dp, ctypes.c_double, vp]
         c.tcfd_ns2d_step_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, dp, dp, dp, ctypes.c_double, vp]
@@ -153,6 +155,11 @@ class NS2DPlan:
     def last_launch_count(self) -> int:
         return int(self.lib.c.tcfd_ns2d_last_launch_count(self._h))
 
+    @property
+    def dataflow(self) -> bool:
+        """True when tcfd_ns2d_step runs as ONE persistent dataflow launch per call."""
+        return bool(self.lib.c.tcfd_ns2d_schedule(self._h))
+
     def check(self):
         """Raise if a kernel of an earlier asynchronous call reported a failure (tcfd_ns2d_check);
         meaningful after the stream was synchronised."""
@@ -200,7 +207,8 @@ class NS2DPlan:
                                              ms, cnt)
         self.lib.check(rc, "tcfd_ns2d_step_timed")
         res = {"steps": steps}
-        for i, k in enumerate(self.KERNEL_KINDS):
+        kinds = ("rows_inv", "flow_call", "rows_fwd", "cols") if self.dataflow else self.KERNEL_KINDS
+        for i, k in enumerate(kinds):
             res[k] = {"launches": cnt[i], "ms_total": ms[i],
                       "us_per_launch": (1e3 * ms[i] / cnt[i]) if cnt[i] else None}
         return res

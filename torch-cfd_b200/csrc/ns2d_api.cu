@@ -66,6 +66,8 @@ struct tcfd_ns2d {
   int* sync_dev = nullptr;   // ticket + per-sample counters
   int* err_host = nullptr;   // mapped pinned word the kernel raises on a dependency time-out
   int* err_dev = nullptr;
+  void* slab = nullptr;      // one allocation behind H, advt, wS, hA, wT, hB (dataflow schedule)
+  tcfd_flow_window_t win{};  // L2 access-policy window over the hot part of the slab
   // measurement mode (tcfd_ns2d_step_timed): every launch is bracketed by events
   bool timed = false;
   std::vector<cudaEvent_t> ev;
@@ -355,7 +357,7 @@ int flow_step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int 
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, static_cast<cudaStream_t>(stream)));
   }
-  const int rc = h->entry.launch_flow(&fp, &h->maps, h->num_sms, stream);
+  const int rc = h->entry.launch_flow(&fp, &h->maps, h->num_sms, stream, &h->win);
   if (h->timed) {
     CUDA_TRY(cudaEventRecord(e1, static_cast<cudaStream_t>(stream)));
     h->ev.push_back(e0);
@@ -438,9 +440,11 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
     int chunk = want >= (double)h->max_batch ? h->max_batch : (int)want;
     if (chunk < 1) chunk = 1;
     // Persistent dataflow schedule (default for N >= 256; TCFD_FLOW=0 selects the two-launch
-    // schedule): the workspaces hold W samples (TCFD_FLOW_W).  Measured on B200 (profiles/r04_*): the
-    // step is latency/issue bound, not DRAM bound, so a window small enough to stay L2-resident
-    // (W ~ 8 at 512^2) loses more to dependency stalls than it saves in DRAM traffic; default W = 64.
+    // schedule): the workspaces hold W samples (TCFD_FLOW_W).  Measured on B200 (profiles/r04_flow_sweep.md):
+    // the step is bound by per-warp instruction latency at 8-10 resident warps per SM, not by DRAM -- a
+    // window small enough to stay L2-resident (W ~ 8 at 512^2, with or without a persisting-L2 access
+    // window) cuts DRAM traffic 3x and gains nothing, while its shorter dependency distance costs
+    // 10-40 %; default W = 64.
     h->flow = h->entry.launch_flow != nullptr;
     if (const char* e = getenv("TCFD_FLOW")) h->flow = h->flow && atoi(e) != 0;
     if (h->flow) {
@@ -460,19 +464,60 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
     const size_t ab = (size_t)h->chunk * (h->n / 4 + 1) * h->n * 4 * h->es;
     // unit-layout state (v2): [B][n/4+1][2][nh] entries of 4 reals
     const size_t ub = (size_t)h->chunk * (h->n / 4 + 1) * 2 * h->nh * 4 * h->es;
-    void** bufs[] = {&h->hA, &h->hB, &h->wS, &h->wT, &h->advt};
-    for (void** b : bufs) {
-      size_t nb = (b == &h->advt && ab > sb) ? ab : sb;
-      if (h->entry.v2 && b != &h->advt) nb = ub;
-      if (!h->entry.v2 && b == &h->wT) continue;
-      if (cudaMalloc(b, nb) != cudaSuccess) { rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed"); break; }
-      h->ws_bytes += nb;
-    }
     // H: [B][nh][n/yt][4][yt] = 4 * nh * n complex per sample
     const size_t hb = (size_t)h->chunk * h->nh * h->n * 4 * 2 * h->es;
-    if (rc == 0) {
-      if (cudaMalloc(&h->H, hb) != cudaSuccess) rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed");
-      else h->ws_bytes += hb;
+    void** bufs[] = {&h->H, &h->advt, &h->wS, &h->hA, &h->wT, &h->hB};  // hot buffers first
+    size_t nbs[6];
+    for (int i = 0; i < 6; ++i) {
+      void** b = bufs[i];
+      size_t nb = (b == &h->advt && ab > sb) ? ab : sb;
+      if (h->entry.v2 && b != &h->advt) nb = ub;
+      if (b == &h->H) nb = hb;
+      if (!h->entry.v2 && b == &h->wT) nb = 0;
+      nbs[i] = (nb + 1023) / 1024 * 1024;
+    }
+    if (rc == 0 && h->flow) {
+      // one slab, so that a single access-policy window covers the buffers the schedule keeps in L2
+      size_t total = 0;
+      for (size_t nb : nbs) total += nb;
+      if (cudaMalloc(&h->slab, total) != cudaSuccess) {
+        rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed");
+      } else {
+        h->ws_bytes += total;
+        size_t off = 0;
+        for (int i = 0; i < 6; ++i) {
+          *bufs[i] = static_cast<unsigned char*>(h->slab) + off;
+          off += nbs[i];
+        }
+        // grouped items (3 double rows / 4 quads per ticket) need a wide window to keep every SM busy
+        h->win.grouped = (h->n >= 512 && h->chunk >= 24) ? 1 : 0;
+#ifndef TCFD_EMU
+        const size_t hot = total - nbs[5];  // everything but hB (used by the two-launch schedule only)
+        int dev = 0, max_persist = 0, max_win = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        // persisting-L2 window over the hot workspace: experiment knob, off by default (no gain measured,
+        // and cudaLimitPersistingL2CacheSize is a device-wide setting)
+        int want_persist = 0;
+        if (const char* e = getenv("TCFD_FLOW_PERSIST")) want_persist = atoi(e);
+        if (want_persist && hot <= (size_t)max_persist && hot <= (size_t)max_win &&
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, hot) == cudaSuccess) {
+          h->win.base = h->slab;
+          h->win.bytes = hot;
+          h->win.hit_ratio = 1.0f;
+        }
+        if (getenv("TCFD_FLOW_VERBOSE"))
+          fprintf(stderr, "tcfd: flow window W=%d hot=%.1f MB max_persist=%.1f MB max_window=%.1f MB persisting=%d\n",
+                  h->chunk, hot / 1e6, max_persist / 1e6, max_win / 1e6, h->win.bytes ? 1 : 0);
+#endif
+      }
+    } else if (rc == 0) {
+      for (int i = 0; i < 6; ++i) {
+        if (!nbs[i]) continue;
+        if (cudaMalloc(bufs[i], nbs[i]) != cudaSuccess) { rc = fail(TCFD_ERR_NOMEM, "workspace allocation failed"); break; }
+        h->ws_bytes += nbs[i];
+      }
     }
     if (rc == 0 && h->entry.v2) rc = make_tile_maps(h);
   }
@@ -488,10 +533,17 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
 
 extern "C" int tcfd_ns2d_destroy(tcfd_ns2d_t* h) {
   if (!h) return TCFD_OK;
-  void* all[] = {h->tw, h->kappa_x, h->kappa_y, h->nil, h->lin, h->filt, h->fhat, h->tab, h->frow, h->tabU, h->maskU, h->wT, h->hA, h->hB,
-                 h->wS, h->H, h->advt, h->stage_in, h->stage_out, h->stage_dw};
+  void* all[] = {h->tw, h->kappa_x, h->kappa_y, h->nil, h->lin, h->filt, h->fhat, h->tab, h->frow, h->tabU, h->maskU,
+                 h->stage_in, h->stage_out, h->stage_dw};
   for (void* p : all)
     if (p) cudaFree(p);
+  if (h->slab) {
+    cudaFree(h->slab);
+  } else {
+    void* ws[] = {h->wT, h->hA, h->hB, h->wS, h->H, h->advt};
+    for (void* p : ws)
+      if (p) cudaFree(p);
+  }
   if (h->sync_dev) cudaFree(h->sync_dev);
   if (h->err_host) cudaFreeHost(h->err_host);
   for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
@@ -539,6 +591,8 @@ extern "C" int tcfd_ns2d_check(const tcfd_ns2d_t* h) {
     return fail(TCFD_ERR_CUDA, "dataflow schedule: a dependency wait timed out in an earlier call; results are invalid");
   return TCFD_OK;
 }
+
+extern "C" int tcfd_ns2d_schedule(const tcfd_ns2d_t* h) { return (h && h->flow) ? 1 : 0; }
 
 extern "C" size_t tcfd_ns2d_workspace_bytes(const tcfd_ns2d_t* h) { return h ? h->ws_bytes : 0; }
 extern "C" int tcfd_ns2d_last_launch_count(const tcfd_ns2d_t* h) { return h ? h->launches : 0; }

@@ -100,6 +100,36 @@ TCFD_D void flow_wait(const int* p, int target, int* err) {
   }
 #endif
 }
+// the caller's arrays are touched once per call: streaming (evict-first) accesses keep them from
+// displacing the workspace window that lives in L2
+template <class T>
+TCFD_D cx<T> flow_ld_stream(const cx<T>* p) {
+#ifndef TCFD_EMU
+  if constexpr (sizeof(T) == 4) {
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+    return cx<T>{v.x, v.y};
+  } else {
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+    return cx<T>{v.x, v.y};
+  }
+#else
+  return *p;
+#endif
+}
+template <class T>
+TCFD_D void flow_st_stream(cx<T>* p, cx<T> v) {
+#ifndef TCFD_EMU
+  if constexpr (sizeof(T) == 4) __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+  else __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+#else
+  *p = v;
+#endif
+}
+TCFD_D void flow_proxy_fence() {
+#ifndef TCFD_EMU
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+}
 template <class V>
 TCFD_D V flow_ld_cg(const V* p) {  // L2-only load: the line may have been rewritten by another SM
 #ifndef TCFD_EMU
@@ -123,7 +153,7 @@ TCFD_D cx<d2> flow_ld_cg(const cx<d2>* p) {
 // One layout for both roles:
 //   cols: [ tile ]                                              [ buf ] [ barriers ]
 //   rows: [ W | H | ADV (advection row / dw/dt reference) | TAB0 | MASK0 | TAB1 | MASK1 ]
-template <class T, int N>
+template <class T, int N, int VB = 1>  // VB: transforms a thread carries side by side (exchange buffer size)
 struct FlowSmem {
   typedef typename pack2<T>::type L;
   typedef RowsSmem<T, N> R;
@@ -138,7 +168,7 @@ struct FlowSmem {
   static constexpr int ROWS_STAGE = OFF_TAB + 2 * TABM;
   static constexpr int AREA = (G::BYTES > ROWS_STAGE ? G::BYTES : ROWS_STAGE);
   static constexpr int OFF_BUF = (AREA + 127) / 128 * 128;
-  static constexpr int OFF_BAR = OFF_BUF + N * (int)sizeof(cx<L>);
+  static constexpr int OFF_BAR = OFF_BUF + VB * N * (int)sizeof(cx<L>);
   static constexpr int BYTES = OFF_BAR + 64 + 1024;  // + slack for the 1 KB alignment of the area
 };
 
@@ -157,8 +187,22 @@ TCFD_D cx<typename lane_traits<L>::scalar> lane_rt(cx<L> v, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+// Timing experiment (-DTCFD_FLOW_VARIANTS builds, MODE 1): the transforms are replaced by one barrier, so
+// the launch measures everything BUT the FFTs (results are meaningless).
+#define FLOW_FFT(DIR, ARR)                                                \
+  do {                                                                    \
+    if constexpr ((MODE & 1) != 0) __syncthreads();                       \
+    else fft_run<L, N, DIR, 1, false, N>(ARR, tw, buf, parity, t, sync);  \
+  } while (0)
+// MODE bit 1: the inverse transforms run two per thread (V = 2: twice the independent work per warp and
+// half the barriers; needs the register budget of 256 resident threads per SM and a 2 N exchange buffer)
+#define FLOW_FFT2(DIR, ARR)                                                   \
+  do {                                                                        \
+    if constexpr ((MODE & 1) != 0) __syncthreads();                           \
+    else fft_run<L, N, DIR, 2, false, 2 * N>(ARR, tw, buf, parity, t, sync);  \
+  } while (0)
 // GR: double rows per rows item, GC: column quads per cols item (GC divides N/4).
-template <class T, int N, int MINB, int GR, int GC>
+template <class T, int N, int MINB, int GR, int GC, int MODE = 0>
 __global__ void __launch_bounds__(N / 8, MINB)
 ns2d_flow_kernel(const FlowParams<T> fp, const
 #ifndef TCFD_EMU
@@ -166,7 +210,8 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
 #endif
                  TileMaps maps) {
   typedef typename pack2<T>::type L;
-  typedef FlowSmem<T, N> S;
+  constexpr bool V2 = (MODE & 2) != 0;
+  typedef FlowSmem<T, N, V2 ? 2 : 1> S;
   typedef typename S::G G;
   typedef typename S::R R;
   constexpr int NT = N / 8, NH = N / 2 + 1, ND = N / 4 + 1, NQ = N / 4;
@@ -219,8 +264,12 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
 #endif
     next_tk = flow_fetch_add(ticket, 1);
     sh[0] = next_tk;
+    sh[2] = 0;
   }
-  int it = 0;  // items processed by this CTA: the ticket mailbox alternates between sh[0] and sh[1]
+  // items processed by this CTA: the mailbox (ticket: sh[0|1], "inputs already staged" flag: sh[2|3])
+  // alternates between two slots
+  int it = 0;
+  unsigned tabsel = 0;  // table block (of two) the next rows unit uses
   unsigned phase_s = 0, phase_t = 0, phase_a = 0, phase_o = 0;
   int* pending = nullptr;  // thread 0: counter of the item whose stores were just fenced by the barrier
   __syncthreads();
@@ -229,6 +278,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
     // here: the previous item is complete (its stores are ordered before the last barrier, shared
     // memory is free) and sh[0] holds this item's ticket
     const int tk = sh[it & 1];
+    const bool staged = sh[2 + (it & 1)] != 0;  // thread 0 issued this item's first loads during the previous item
     ++it;
     if (t == 0) {
       if (pending) flow_signal(pending);
@@ -236,28 +286,80 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
       next_tk = flow_fetch_add(ticket, 1);  // consumed at the end of this item
     }
     // ---- decode (chunks are equal-sized except the last)
-    const int c = (int)((long long)tk / per_chunk);
-    if (c >= nchunks) break;
-    const int Wc = (c == nchunks - 1) ? p.B - c * W : W;
-    int r = (int)((long long)tk - (long long)c * per_chunk);
-    if (r >= Wc * (IR + nsub * per_pair)) break;  // past the end (last chunk)
+    // ticket -> chunk c, its size Wc, kind, substage j (-1 = prologue), item index u inside the phase
+    auto decode = [&](int tkt, int& c_, int& Wc_, bool& rows_, int& j_, int& u_) -> bool {
+      c_ = (int)((long long)tkt / per_chunk);
+      if (c_ >= nchunks) return false;
+      Wc_ = (c_ == nchunks - 1) ? p.B - c_ * W : W;
+      int r = (int)((long long)tkt - (long long)c_ * per_chunk);
+      if (r >= Wc_ * (IR + nsub * per_pair)) return false;  // past the end (last chunk)
+      if (r < Wc_ * IR) {
+        rows_ = true; j_ = -1; u_ = r;
+      } else {
+        r -= Wc_ * IR;
+        j_ = r / (Wc_ * per_pair);
+        const int q = r % (Wc_ * per_pair);
+        rows_ = q >= Wc_ * IC;
+        u_ = rows_ ? q - Wc_ * IC : q;
+      }
+      return true;
+    };
+    int c, Wc, j, u;
     bool is_rows;
-    int j, u;  // substage (-1 = prologue), item index inside the phase
-    if (r < Wc * IR) {
-      is_rows = true; j = -1; u = r;
-    } else {
-      r -= Wc * IR;
-      j = r / (Wc * per_pair);
-      const int q = r % (Wc * per_pair);
-      is_rows = q >= Wc * IC;
-      u = is_rows ? q - Wc * IC : q;
-    }
+    if (!decode(tk, c, Wc, is_rows, j, u)) break;
+
+    // one thread: stage the inputs of unit d of slot sl_ -- its table block always, state and advection
+    // row for substage items
+    auto issue_unit = [&](int sl_, int d, unsigned sel, bool prologue_, bool rd_h_) {
+      unsigned char* tabdst = area + S::OFF_TAB + sel * S::TABM;
+      stage_expect(bar_t, (unsigned)S::TABM);
+      bulk_load(tabdst, reinterpret_cast<const unsigned char*>(p.tabU) + (size_t)d * R::TAB_BYTES, (unsigned)R::TAB_BYTES, bar_t);
+      bulk_load(tabdst + R::TAB_BYTES, p.maskU + (size_t)d * 2 * R::MASK_ROW, (unsigned)(2 * R::MASK_ROW), bar_t);
+      if (!prologue_) {
+        const size_t ub_ = ((size_t)sl_ * ND + d) * 2 * NH;
+        stage_expect(bar_s, (unsigned)R::UNIT_BYTES * (1u + (rd_h_ ? 1u : 0u)));
+        bulk_load(area + S::OFF_W, fp.wU + ub_, (unsigned)R::UNIT_BYTES, bar_s);
+        if (rd_h_) bulk_load(area + S::OFF_H, fp.hU + ub_, (unsigned)R::UNIT_BYTES, bar_s);
+        if (d < p.NDF) {
+          stage_expect(bar_a, (unsigned)(N * sizeof(cx<L>)));
+          bulk_load(area + S::OFF_ADV, reinterpret_cast<const cx<L>*>(p.advt2) + ((size_t)sl_ * ND + d) * N,
+                    (unsigned)(N * sizeof(cx<L>)), bar_a);
+        }
+      }
+    };
+    // one thread, at a point of the current item where the staging area of the next item is free
+    // (cols: tile consumed; rows: state / advection stages consumed and the other table block idle):
+    // if the next ticket's dependency is ALREADY satisfied, start its first loads now.  Never waits.
+    int staged_next = 0;
+    auto try_stage_next = [&](bool cur_is_rows) {
+      int c2, W2, j2, u2;
+      bool rows2;
+      if (!decode(next_tk, c2, W2, rows2, j2, u2)) return;
+      if (cur_is_rows && !rows2) return;  // the tile would overwrite the table block still in use
+      if (!rows2) {
+        const int sl2 = u2 / IC, s2 = c2 * W + sl2;
+        if (flow_ld_acquire(&cnt_rows[s2]) < IR * (j2 + 1)) return;
+        flow_proxy_fence();
+        tile_load_issue<NH, IB>(tile, maps, (u2 % IC) * GC * 4, sl2, bar_s);
+      } else {
+        const int sl2 = u2 / IR, s2 = c2 * W + sl2;
+        const bool pro2 = j2 < 0;
+        if (pro2) {
+          if (s2 >= W && flow_ld_acquire(&cnt_rows[s2 - W]) < IR * (nsub + 1)) return;
+        } else {
+          if (flow_ld_acquire(&cnt_cols[s2]) < IC * (j2 + 1)) return;
+        }
+        flow_proxy_fence();
+        issue_unit(sl2, (u2 % IR) * GR, cur_is_rows ? (tabsel ^ 1u) : tabsel, pro2, !pro2 && fp.rd_h[j2 % fp.nstages]);
+      }
+      staged_next = 1;
+    };
 
     if (!is_rows) {
       // ================================================================= cols item: GC quads
       const int sl = u / IC, q0 = (u % IC) * GC;  // slot inside the chunk, first quad
       const int s = c * W + sl;
-      if (t == 0) {
+      if (t == 0 && !staged) {
         flow_wait(&cnt_rows[s], IR * (j + 1), fp.err);
         tile_load_issue<NH, IB>(tile, maps, q0 * 4, sl, bar_s);
       }
@@ -267,34 +369,71 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         cx<L> cc[1][8];
         tile_load_wait(bar_s, phase_s);
         phase_s ^= 1u;
+        if constexpr (V2) {
 #pragma unroll
-        for (int cidx = 0; cidx < 4; ++cidx) {
-          cx<L> z[1][8];
+          for (int pr = 0; pr < 2; ++pr) {
+            cx<L> z[2][8];
 #pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const int k = t + m * NT;
-            const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
-            const int row = lo ? k : N - k;
-            const cx<L> A = tile_ld<T, G>(tile, row, 0, cidx);
-            const cx<L> Bv = tile_ld<T, G>(tile, row, 1, cidx);
-            z[0][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
-            if ((m == 0 || m == 4) && t == 0) z[0][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
+            for (int v = 0; v < 2; ++v)
+#pragma unroll
+              for (int m = 0; m < 8; ++m) {
+                const int k = t + m * NT;
+                const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
+                const int row = lo ? k : N - k;
+                const cx<L> A = tile_ld<T, G>(tile, row, 0, 2 * pr + v);
+                const cx<L> Bv = tile_ld<T, G>(tile, row, 1, 2 * pr + v);
+                z[v][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
+                if ((m == 0 || m == 4) && t == 0) z[v][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
+              }
+            FLOW_FFT2(+1, z);
+            if (pr == 1) {
+              // every thread has passed a barrier after its last tile read: the tile is free
+              if (t == 0) {
+                if (g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
+                else try_stage_next(false);
+              }
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const T adv0 = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
+              const T adv1 = -(z[1][m].x.hi * z[1][m].x.lo + z[1][m].y.hi * z[1][m].y.lo);
+              if (pr == 0) { cc[0][m].x.lo = adv0; cc[0][m].y.lo = adv1; }
+              else { cc[0][m].x.hi = adv0; cc[0][m].y.hi = adv1; }
+            }
           }
-          fft_run<L, N, +1, 1, false, N>(z, tw, buf, parity, t, sync);
-          if (cidx == 3) {
-            // every thread has passed a barrier after its last tile read: the tile is free
-            if (t == 0 && g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
-          }
+        } else {
 #pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const T adv = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
-            if (cidx == 0) cc[0][m].x.lo = adv;
-            if (cidx == 1) cc[0][m].y.lo = adv;
-            if (cidx == 2) cc[0][m].x.hi = adv;
-            if (cidx == 3) cc[0][m].y.hi = adv;
+          for (int cidx = 0; cidx < 4; ++cidx) {
+            cx<L> z[1][8];
+  #pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const int k = t + m * NT;
+              const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
+              const int row = lo ? k : N - k;
+              const cx<L> A = tile_ld<T, G>(tile, row, 0, cidx);
+              const cx<L> Bv = tile_ld<T, G>(tile, row, 1, cidx);
+              z[0][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
+              if ((m == 0 || m == 4) && t == 0) z[0][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
+            }
+            FLOW_FFT(+1, z);
+            if (cidx == 3) {
+              // every thread has passed a barrier after its last tile read: the tile is free
+              if (t == 0) {
+                if (g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
+                else try_stage_next(false);
+              }
+            }
+  #pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const T adv = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
+              if (cidx == 0) cc[0][m].x.lo = adv;
+              if (cidx == 1) cc[0][m].y.lo = adv;
+              if (cidx == 2) cc[0][m].x.hi = adv;
+              if (cidx == 3) cc[0][m].y.hi = adv;
+            }
           }
         }
-        fft_run<L, N, -1, 1, false, N>(cc, tw, buf, parity, t, sync);
+        FLOW_FFT(-1, cc);
 #pragma unroll
         for (int m = 0; m < 8; ++m) buf[t + m * NT] = cc[0][m];
         __syncthreads();
@@ -315,6 +454,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
       }
       if (t == 0) {
         sh[it & 1] = next_tk;
+        sh[2 + (it & 1)] = staged_next;
         pending = &cnt_cols[s];
       }
       __syncthreads();
@@ -334,32 +474,13 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
     const size_t sb = (size_t)s * N * NH;  // reference layout: sample base
     const T beta = fp.beta[k], gdt = fp.gdt[k], mu = fp.mu[k];
 
-    // one thread: stage the inputs of unit d (unit index g inside the item) -- tables always, state and
-    // advection row for substage items
-    auto issue_unit = [&](int d, int g) {
-      unsigned char* tabdst = area + S::OFF_TAB + (g & 1) * S::TABM;
-      stage_expect(bar_t, (unsigned)S::TABM);
-      bulk_load(tabdst, reinterpret_cast<const unsigned char*>(p.tabU) + (size_t)d * R::TAB_BYTES, (unsigned)R::TAB_BYTES, bar_t);
-      bulk_load(tabdst + R::TAB_BYTES, p.maskU + (size_t)d * 2 * R::MASK_ROW, (unsigned)(2 * R::MASK_ROW), bar_t);
-      if (!prologue) {
-        const size_t ub = ((size_t)sl * ND + d) * 2 * NH;
-        stage_expect(bar_s, (unsigned)R::UNIT_BYTES * (1u + (rd_h ? 1u : 0u)));
-        bulk_load(area + S::OFF_W, fp.wU + ub, (unsigned)R::UNIT_BYTES, bar_s);
-        if (rd_h) bulk_load(area + S::OFF_H, fp.hU + ub, (unsigned)R::UNIT_BYTES, bar_s);
-        if (d < p.NDF) {
-          stage_expect(bar_a, (unsigned)(N * sizeof(cx<L>)));
-          bulk_load(area + S::OFF_ADV, reinterpret_cast<const cx<L>*>(p.advt2) + ((size_t)sl * ND + d) * N,
-                    (unsigned)(N * sizeof(cx<L>)), bar_a);
-        }
-      }
-    };
-    if (t == 0) {
+    if (t == 0 && !staged) {
       if (prologue) {
         if (s >= W) flow_wait(&cnt_rows[s - W], IR * (nsub + 1), fp.err);
       } else {
         flow_wait(&cnt_cols[s], IC * (j + 1), fp.err);
       }
-      issue_unit(d0, 0);
+      issue_unit(sl, d0, tabsel, prologue, rd_h);
     }
 
 #pragma unroll 1
@@ -371,7 +492,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
       const int r1b = valid1 ? 2 * d + 1 : r1a, r2b = (N - r1b) % N;
       const bool selfa = r1a == r2a, selfb = r1b == r2b;
       const T kx1a = p.kappa_x[r1a], kx2a = p.kappa_x[r2a], kx1b = p.kappa_x[r1b], kx2b = p.kappa_x[r2b];
-      const unsigned char* tabsrc = area + S::OFF_TAB + (g & 1) * S::TABM;
+      const unsigned char* tabsrc = area + S::OFF_TAB + tabsel * S::TABM;
       const L* linst = reinterpret_cast<const L*>(tabsrc);
       const T* nilst = reinterpret_cast<const T*>(tabsrc) + 2 * NH;
       const unsigned char* maskst = tabsrc + R::TAB_BYTES;
@@ -383,13 +504,14 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
           const bool lo = m < 4;
-          const cx<T> w0 = w[lo ? lo_a + m * NT : hi_a - m * NT], w1 = w[lo ? lo_b + m * NT : hi_b - m * NT];
+          const cx<T> w0 = flow_ld_stream(w + (lo ? lo_a + m * NT : hi_a - m * NT)),
+                      w1 = flow_ld_stream(w + (lo ? lo_b + m * NT : hi_b - m * NT));
           wv[m] = cx<L>{L(w0.x, w1.x), L(w0.y, w1.y)};
         }
         if (t == 0) {
-          const cx<T> a0 = w[r2a * NH], a1 = w[r2b * NH];
+          const cx<T> a0 = flow_ld_stream(w + r2a * NH), a1 = flow_ld_stream(w + r2b * NH);
           e0 = cx<L>{L(a0.x, a1.x), L(a0.y, a1.y)};
-          const cx<T> b0 = w[r1a * NH + N / 2], b1 = w[r1b * NH + N / 2];
+          const cx<T> b0 = flow_ld_stream(w + r1a * NH + N / 2), b1 = flow_ld_stream(w + r1b * NH + N / 2);
           e1 = cx<L>{L(b0.x, b1.x), L(b0.y, b1.y)};
         }
         // the table block was issued by thread 0 AFTER its dependency wait: its arrival also tells
@@ -418,7 +540,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
           phase_a ^= 1u;
 #pragma unroll
           for (int m = 0; m < 8; ++m) a[0][m] = advst[t + m * NT];
-          fft_run<L, N, -1, 1, false, N>(a, tw, buf, parity, t, sync);
+          FLOW_FFT(-1, a);
         } else {
 #pragma unroll
           for (int m = 0; m < 8; ++m) a[0][m] = cx<L>{L(T(0)), L(T(0))};
@@ -460,12 +582,12 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
           const cx<L> x = (w + L(gdt) * h) + L(mu) * (lin * w);
           const cx<L> wn = inv * x;
           if (last_sub) {
-            if (own_a) p.w_out[sb + ra * NH + col] = cx<T>{wn.x.lo, wn.y.lo};
-            if (own_b) p.w_out[sb + rb * NH + col] = cx<T>{wn.x.hi, wn.y.hi};
+            if (own_a) flow_st_stream(p.w_out + sb + ra * NH + col, cx<T>{wn.x.lo, wn.y.lo});
+            if (own_b) flow_st_stream(p.w_out + sb + rb * NH + col, cx<T>{wn.x.hi, wn.y.hi});
             if (want_dwdt) {
               const cx<L> o = advst[half * NH + col];
-              if (own_a) p.dwdt[sb + ra * NH + col] = cx<T>{p.inv_tdt * (wn.x.lo - o.x.lo), p.inv_tdt * (wn.y.lo - o.y.lo)};
-              if (own_b) p.dwdt[sb + rb * NH + col] = cx<T>{p.inv_tdt * (wn.x.hi - o.x.hi), p.inv_tdt * (wn.y.hi - o.y.hi)};
+              if (own_a) flow_st_stream(p.dwdt + sb + ra * NH + col, cx<T>{p.inv_tdt * (wn.x.lo - o.x.lo), p.inv_tdt * (wn.y.lo - o.y.lo)});
+              if (own_b) flow_st_stream(p.dwdt + sb + rb * NH + col, cx<T>{p.inv_tdt * (wn.x.hi - o.x.hi), p.inv_tdt * (wn.y.hi - o.y.hi)});
             }
           } else {
             fp.wU[ub + half * NH + col] = wn;
@@ -486,14 +608,54 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
       }
       // the W / H / ADV stages are consumed (and the other table block has been free since the
       // previous unit's inverse transforms): stage the next unit under this unit's inverse transforms
-      if (g + 1 < gn) {
-        __syncthreads();
-        if (t == 0) issue_unit(d + 1, g + 1);
+      __syncthreads();
+      if (t == 0) {
+        if (g + 1 < gn) issue_unit(sl, d + 1, tabsel ^ 1u, prologue, rd_h);
+        else try_stage_next(true);
       }
+      tabsel ^= 1u;
 
       if (do_inv) {
-        const int nq = valid1 ? 4 : 2;
         const T ky0 = p.kappa_y[0], kyh = p.kappa_y[N / 2];
+        if constexpr (V2) {
+          // both halves of a lane side by side: (u, dw/dx) -> plane 0, (v, dw/dy) -> plane 1
+#pragma unroll 1
+          for (int lane = 0; lane < (valid1 ? 2 : 1); ++lane) {
+            const T kx1 = lane ? kx1b : kx1a, kx2 = lane ? kx2b : kx2a;
+            const int r1 = lane ? r1b : r1a;
+            const T* nl = nilst + lane * NH;
+            cx<L> z[2][8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const bool lo = m < 4;
+              const T kx = lo ? kx1 : kx2;
+              const T nil = nl[lo ? t + m * NT : N - t - m * NT];
+              const cx<T> wl = lane_rt(wv[m], lane);
+              const cx<L> f0 = ns_fields_rt<T>(wl, nil, kyv[m], kx), f1 = ns_fields_rt<T>(wl, nil, -kx, kyv[m]);
+              z[0][m] = lo ? f0 : conj(f0);
+              z[1][m] = lo ? f1 : conj(f1);
+            }
+            if (t == 0) {
+              const T n0 = nl[0], nh = nl[N / 2];
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const cx<L> f1 = ns_fields_rt<T>(lane_rt(wv[0], lane), n0, half ? -kx1 : ky0, half ? ky0 : kx1);
+                const cx<L> f2_ = ns_fields_rt<T>(lane_rt(e0, lane), n0, half ? -kx2 : ky0, half ? ky0 : kx2);
+                const cx<L> g1 = ns_fields_rt<T>(lane_rt(e1, lane), nh, half ? -kx1 : kyh, half ? kyh : kx1);
+                const cx<L> g2 = ns_fields_rt<T>(lane_rt(wv[4], lane), nh, half ? -kx2 : kyh, half ? kyh : kx2);
+                z[half][0] = L(T(0.5)) * (f1 + conj(f2_));
+                z[half][4] = L(T(0.5)) * (g1 + conj(g2));
+              }
+            }
+            FLOW_FFT2(+1, z);
+            cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + ((size_t)sl * NH + r1) * (size_t)N + t;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) Hrow[m * NT] = z[0][m];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) Hrow[p.Hplane + m * NT] = z[1][m];
+          }
+        } else {
+          const int nq = valid1 ? 4 : 2;
 #pragma unroll 1
         for (int q = 0; q < nq; ++q) {
           const int lane = q >> 1, half = q & 1;
@@ -519,15 +681,17 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
             z[0][0] = L(T(0.5)) * (f1 + conj(f2_));
             z[0][4] = L(T(0.5)) * (g1 + conj(g2));
           }
-          fft_run<L, N, +1, 1, false, N>(z, tw, buf, parity, t, sync);
+          FLOW_FFT(+1, z);
           cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + (size_t)half * p.Hplane + ((size_t)sl * NH + r1) * (size_t)N + t;
 #pragma unroll
           for (int m = 0; m < 8; ++m) Hrow[m * NT] = z[0][m];
+        }
         }
       }
     }
     if (t == 0) {
       sh[it & 1] = next_tk;
+      sh[2 + (it & 1)] = staged_next;
       pending = &cnt_rows[s];
     }
     __syncthreads();

@@ -177,45 +177,82 @@ int launch(int which, const NsParams<real_t>& p, const TileMaps* maps, int num_s
 #ifndef TCFD_FLOW_MINB
 #define TCFD_FLOW_MINB MINB_BY_THREADS
 #endif
-constexpr size_t FLOW_SMEM = (size_t)FlowSmem<real_t, N>::BYTES;
+constexpr size_t FLOW_SMEM = (size_t)FlowSmem<real_t, N>::BYTES;       // single-transform exchange buffer
+constexpr size_t FLOW_SMEM2 = (size_t)FlowSmem<real_t, N, 2>::BYTES;   // two transforms per thread
 constexpr int FLOW_BY_SMEM = (int)(232448 / (FLOW_SMEM + 1024));
 constexpr int FLOW_MINB = FLOW_BY_SMEM < 1 ? 1 : (FLOW_BY_SMEM < TCFD_FLOW_MINB ? FLOW_BY_SMEM : TCFD_FLOW_MINB);
 
-template <int GR, int GC, int MAXR>
-int launch_flow_g(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms, cudaStream_t stream) {
+// MAXR: CTAs per SM the register budget is tuned for (0 = FLOW_MINB)
+template <int GR, int GC, int MAXR, int MODE = 0>
+int launch_flow_g(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms, cudaStream_t stream,
+                  const tcfd_flow_window_t* win) {
   static int occ = 0;
-  auto k = ns2d_flow_kernel<real_t, N, FLOW_MINB, GR, GC>;
+  auto k = ns2d_flow_kernel<real_t, N, (MAXR > 0 ? MAXR : FLOW_MINB), GR, GC, MODE>;
+  constexpr size_t smem = (MODE & 2) ? FLOW_SMEM2 : FLOW_SMEM;
   int rc = 0;
-  if (!occ && (rc = prep(k, FLOW_SMEM, NT, &occ))) return rc;
+  if (!occ && (rc = prep(k, smem, NT, &occ))) return rc;
 #ifdef TCFD_EMU
+  (void)win;
   const int grid = 2;
-#else
-  const int grid = num_sms * occ;
-#endif
-  TCFD_LAUNCH(k, grid, NT, FLOW_SMEM, stream, fp, *maps);
+  TCFD_LAUNCH(k, grid, NT, smem, stream, fp, *maps);
   return 0;
+#else
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(num_sms * occ));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (win && win->bytes) {
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = win->base;
+    attr[0].val.accessPolicyWindow.num_bytes = win->bytes;
+    attr[0].val.accessPolicyWindow.hitRatio = win->hit_ratio;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return (int)cudaLaunchKernelEx(&cfg, k, fp, *maps);
+#endif
 }
 
-// group sizes (double rows per rows item, column quads per cols item) and register cap (0: from
-// __launch_bounds__); TCFD_FLOW_G="<GR>,<GC>,<MAXR>" selects one of the other compiled variants
+// group sizes (double rows per rows item, column quads per cols item) and CTAs per SM of the register
+// budget (0: FLOW_MINB); TCFD_FLOW_G="<GR>,<GC>,<MINB>" selects one of the other compiled variants
 // (schedule experiments, -DTCFD_FLOW_VARIANTS builds only)
-int launch_flow(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms, cudaStream_t stream) {
+int launch_flow(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms, cudaStream_t stream,
+                const tcfd_flow_window_t* win) {
   if (!maps) return -2;
-  static int gr = 0, gc = 0, mr = 0;
-  if (!gr) {
-    gr = 1;
-    gc = 1;
+  // Items: grouped (3 double rows / 4 column quads per ticket, register budget for 256 resident threads
+  // per SM -> no spills) when the window is wide, single units when it is narrow (a narrow window needs
+  // every item it can get to keep the SMs busy).  The caller chooses (win->grouped); TCFD_FLOW_G=
+  // "<GR>,<GC>,<MINB>" selects any compiled variant (-DTCFD_FLOW_VARIANTS builds: schedule experiments).
+  constexpr int MR_RAW = (sizeof(real_t) == 4 ? 256 : 128) / NT;
+  constexpr int MR = MR_RAW < 1 ? 1 : MR_RAW;
+  int gr = (win && win->grouped) ? 3 : 1, gc = (win && win->grouped) ? 4 : 1, mr = MR;
+  static int egr = -1, egc = 0, emr = 0;
+  if (egr < 0) {
+    egr = 0;
     if (const char* e = getenv("TCFD_FLOW_G")) {
       int a = 0, b = 0, c = 0;
       const int nf = sscanf(e, "%d,%d,%d", &a, &b, &c);
-      if (nf >= 2) { gr = a; gc = b; mr = nf == 3 ? c : 0; }
+      if (nf >= 2) { egr = a; egc = b; emr = nf == 3 ? c : 0; }
     }
   }
-#define TCFD_FLOW_CASE(A, B, C) if (gr == A && gc == B && mr == C) return launch_flow_g<A, B, C>(fp, maps, num_sms, stream);
-  TCFD_FLOW_CASE(1, 1, 0)
+  if (egr > 0) { gr = egr; gc = egc; mr = emr; }
+#define TCFD_FLOW_CASE(A, B, C) if (gr == A && gc == B && mr == C) return launch_flow_g<A, B, C>(fp, maps, num_sms, stream, win);
+  TCFD_FLOW_CASE(3, 4, MR)
+  TCFD_FLOW_CASE(1, 1, MR)
 #ifdef TCFD_FLOW_VARIANTS
+  TCFD_FLOW_CASE(1, 1, 0)
   TCFD_FLOW_CASE(3, 4, 0)
-  TCFD_FLOW_CASE(2, 2, 0)
+  TCFD_FLOW_CASE(2, 2, MR)
+  if (gr == 3 && gc == 4 && mr == -4) return launch_flow_g<3, 4, MR, 1>(fp, maps, num_sms, stream, win);  // no-FFT timing
+  if (gr == 1 && gc == 1 && mr == -4) return launch_flow_g<1, 1, MR, 1>(fp, maps, num_sms, stream, win);
+  // two inverse transforms per thread (V = 2)
+  if (gr == 3 && gc == 4 && mr == 2) return launch_flow_g<3, 4, MR, 2>(fp, maps, num_sms, stream, win);
+  if (gr == 1 && gc == 1 && mr == 2) return launch_flow_g<1, 1, MR, 2>(fp, maps, num_sms, stream, win);
+  if (gr == 3 && gc == 4 && mr == -2) return launch_flow_g<3, 4, MR, 3>(fp, maps, num_sms, stream, win);
 #endif
 #undef TCFD_FLOW_CASE
   return -3;
@@ -242,9 +279,9 @@ int launch(int which, const void* params, const void* maps, int num_sms, void* s
 }
 
 #if TCFD_N >= 256
-int launch_flow(const void* params, const void* maps, int num_sms, void* stream_) {
+int launch_flow(const void* params, const void* maps, int num_sms, void* stream_, const tcfd_flow_window_t* win) {
   int rc = v2::launch_flow(*static_cast<const FlowParams<real_t>*>(params), static_cast<const TileMaps*>(maps), num_sms,
-                           static_cast<cudaStream_t>(stream_));
+                           static_cast<cudaStream_t>(stream_), win);
   if (rc) return rc;
 #ifndef TCFD_EMU
   return (int)cudaGetLastError();
