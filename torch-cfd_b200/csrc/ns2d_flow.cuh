@@ -414,6 +414,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
               const cx<L> Bv = tile_ld<T, G>(tile, row, 1, cidx);
               z[0][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
               if ((m == 0 || m == 4) && t == 0) z[0][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
+              if constexpr ((MODE & 8) != 0) z[0][m] = (m & 1) ? A : Bv;  // timing experiment: no unpack math
             }
             FLOW_FFT(+1, z);
             if (cidx == 3) {
@@ -564,6 +565,13 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         }
         // RK / CN update of entry (half, col) in both lanes; returns the new w
         auto update = [&](int half, int col, cx<L> A, bool own_a, bool own_b) -> cx<L> {
+          if constexpr ((MODE & 16) != 0) {  // timing experiment: loads and stores only
+            const cx<L> w_ = wst[half * NH + col];
+            const cx<L> wn_ = A + w_;
+            fp.wU[ub + half * NH + col] = wn_;
+            if (wr_h) fp.hU[ub + half * NH + col] = A;
+            return wn_;
+          }
           const int ra = half ? r2a : r1a, rb = half ? r2b : r1b;
           const L lin = linst[col];
           const unsigned mk = maskst[half * R::MASK_ROW + col];
@@ -668,10 +676,14 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
             const bool lo = m < 4;
             const T kx = lo ? kx1 : kx2;
             const T nil = nl[lo ? t + m * NT : N - t - m * NT];
+            if constexpr ((MODE & 4) != 0) {  // timing experiment: no field construction
+              z[0][m] = wv[m];
+              continue;
+            }
             const cx<L> f = ns_fields_rt<T>(lane_rt(wv[m], lane), nil, half ? -kx : kyv[m], half ? kyv[m] : kx);
             z[0][m] = lo ? f : conj(f);
           }
-          if (t == 0) {
+          if (t == 0 && (MODE & 4) == 0) {
             // self-conjugate columns ky = 0 and ky = N/2: Hermitian part of the two rows (C2R semantics)
             const T n0 = nl[0], nh = nl[N / 2];
             const cx<L> f1 = ns_fields_rt<T>(lane_rt(wv[0], lane), n0, half ? -kx1 : ky0, half ? ky0 : kx1);
