@@ -93,6 +93,55 @@ int launch_planes_inv(const cplx* Z2, float* y, const cplx* Sy, const cplx* tw, 
   TCFD_LAUNCH(k, (nplanes + S::GP - 1) / S::GP, S::GP * S::NT, smem, st, Z2, y, Sy, tw, d, nplanes);
   return 0;
 }
+// second-generation plane kernels: persistent grid (SM count x resident CTAs), pipelined staging
+int planes_grid(const void* kernel, int threads, size_t smem, int want) {
+#ifndef TCFD_EMU
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  const int cap = sms * occ;
+  return want < cap ? want : cap;
+#else
+  (void)kernel; (void)threads; (void)smem;
+  return want < 3 ? want : 3;  // several planes per group: exercises the double buffering
+#endif
+}
+bool planes_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TCFD_SCONV_PLANES");
+    v = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return v == 1;
+}
+template <int Y>
+int launch_planes_fwd2(const float* x, cplx* Z1, const cplx* A, const cplx* tw, SconvDims d, int nplanes, cudaStream_t st) {
+  typedef Planes2Smem<Y> S;
+  const size_t smem = S::table_bytes(d.Tin, d.mt) + S::GP * S::group_bytes(d.Tin, d.my, d.mt, false);
+  // bulk copies need 16-byte aligned planes (always true for whole tensors; a sliced view may not be)
+  if (smem > 227 * 1024 || (reinterpret_cast<uintptr_t>(x) & 15u)) return launch_planes_fwd<Y>(x, Z1, A, tw, d, nplanes, st);
+  auto k = sconv_planes_fwd2_kernel<Y>;
+  if (int rc = set_smem(k, smem)) return rc;
+  const int grid = planes_grid(reinterpret_cast<const void*>(k), S::GP * S::NT, smem, (nplanes + S::GP - 1) / S::GP);
+  TCFD_LAUNCH(k, grid, S::GP * S::NT, smem, st, x, Z1, A, tw, d, nplanes);
+  return 0;
+}
+template <int Y>
+int launch_planes_inv2(const cplx* Z2, float* y, const cplx* Sy, const cplx* tw, SconvDims d, int nplanes, cudaStream_t st) {
+  typedef Planes2Smem<Y> S;
+  const size_t smem = S::table_bytes(d.Tout, d.mt) + S::GP * S::group_bytes(d.Tout, d.my, d.mt, true);
+  if (smem > 227 * 1024 || (reinterpret_cast<uintptr_t>(y) & 15u)) return launch_planes_inv<Y>(Z2, y, Sy, tw, d, nplanes, st);
+  auto k = sconv_planes_inv2_kernel<Y>;
+  if (int rc = set_smem(k, smem)) return rc;
+  const int grid = planes_grid(reinterpret_cast<const void*>(k), S::GP * S::NT, smem, (nplanes + S::GP - 1) / S::GP);
+  TCFD_LAUNCH(k, grid, S::GP * S::NT, smem, st, Z2, y, Sy, tw, d, nplanes);
+  return 0;
+}
 template <int X, bool FWD>
 int launch_xaxis(const cplx* in, cplx* out, const cplx* tw, SconvDims d, int ncol, int nslabs, cudaStream_t st) {
   typedef XaxisSmem<X> S;
@@ -106,13 +155,13 @@ int launch_xaxis(const cplx* in, cplx* out, const cplx* tw, SconvDims d, int nco
 #define SCONV_SIZES(F) F(32) F(64) F(128) F(256) F(512)
 
 int planes_fwd(int Y, const float* x, cplx* Z1, const cplx* A, const cplx* tw, SconvDims d, int np, cudaStream_t st) {
-#define CASE(n) if (Y == n) return launch_planes_fwd<n>(x, Z1, A, tw, d, np, st);
+#define CASE(n) if (Y == n) return planes_v1() ? launch_planes_fwd<n>(x, Z1, A, tw, d, np, st) : launch_planes_fwd2<n>(x, Z1, A, tw, d, np, st);
   SCONV_SIZES(CASE)
 #undef CASE
   return -1;
 }
 int planes_inv(int Y, const cplx* Z2, float* y, const cplx* Sy, const cplx* tw, SconvDims d, int np, cudaStream_t st) {
-#define CASE(n) if (Y == n) return launch_planes_inv<n>(Z2, y, Sy, tw, d, np, st);
+#define CASE(n) if (Y == n) return planes_v1() ? launch_planes_inv<n>(Z2, y, Sy, tw, d, np, st) : launch_planes_inv2<n>(Z2, y, Sy, tw, d, np, st);
   SCONV_SIZES(CASE)
 #undef CASE
   return -1;
@@ -249,7 +298,7 @@ extern "C" int tcfd_sconv3d_forward(tcfd_sconv3d_t* h, const void* x, const void
     a.bias[c] = bias ? static_cast<const cplx*>(bias[c]) : nullptr;
   }
   a.B = batch; a.Ci = d.Ci; a.Co = d.Co; a.delta = delta;
-  TCFD_LAUNCH3(sconv_mix_fwd_kernel, (h->K + 127) / 128, d.Co, 1, 128, 0, st, Xh, Yh, a, dm);
+  TCFD_LAUNCH3(sconv_mix_fwd_kernel, (h->K + 127) / 128, (d.Co + MIX_OT - 1) / MIX_OT, 1, 128, 0, st, Xh, Yh, a, dm);
   if ((rc = check_launch(h, 0, "mix_fwd"))) return rc;
   dm = dims_of(h, d.T_in, d.T_out, batch * d.Co);
   rc = check_launch(h, xaxis(d.X, false, Yh, Z, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Co, st), "xaxis_inv");
@@ -294,7 +343,7 @@ extern "C" int tcfd_sconv3d_backward(tcfd_sconv3d_t* h, const void* grad_y, cons
     if ((rc = check_launch(h, 0, "mix_bwd_w"))) return rc;
   }
   if (grad_x) {
-    TCFD_LAUNCH3(sconv_mix_bwd_x_kernel, (h->K + 127) / 128, d.Ci, 1, 128, 0, st, gYh, gXh, a, dm);
+    TCFD_LAUNCH3(sconv_mix_bwd_x_kernel, (h->K + 127) / 128, (d.Ci + MIX_OT - 1) / MIX_OT, 1, 128, 0, st, gYh, gXh, a, dm);
     if ((rc = check_launch(h, 0, "mix_bwd_x"))) return rc;
     dm = dims_of(h, d.T_out, d.T_in, batch * d.Ci);
     rc = check_launch(h, xaxis(d.X, false, gXh, Z, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Ci, st), "xaxis_inv(bwd)");

@@ -19,6 +19,7 @@
 // kernels with conjugate-transposed tables (see sconv_api.cu).
 #pragma once
 #include "fft_core.cuh"
+#include "tma.cuh"
 
 namespace tcfd {
 
@@ -219,6 +220,242 @@ sconv_planes_inv_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y,
 }
 
 // ------------------------------------------------------------------------------------------
+// Pipelined plane kernels (second generation).  Same arithmetic as the two kernels above, but
+//   * persistent: a group walks over planes, the grid is sized to the SM count;
+//   * the plane (forward) / its truncated spectrum block (inverse) of the NEXT plane is staged by a bulk
+//     copy (TMA engine, mbarrier completion) while the current plane is transformed; the inverse kernel
+//     writes its output plane with a bulk store from a double-buffered tile;
+//   * groups synchronise among themselves only (a group is one warp for Y <= 256: __syncwarp; a named
+//     barrier for Y = 512), so the groups of a CTA de-synchronise and hide each other's latencies;
+//   * the t-axis tables live in shared memory.
+template <int NT>
+struct GroupSync {
+  int id;
+  TCFD_D void operator()() const {
+#ifndef TCFD_EMU
+    if constexpr (NT <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(NT) : "memory");
+#else
+    __syncthreads();
+#endif
+  }
+};
+
+template <int Y>
+struct Planes2Smem {
+  static constexpr int NT = Y / 8;
+  // two groups per CTA (at least one warp): shared memory, not the CTA shape, bounds the residency
+  static constexpr int GP = (64 / NT) > 0 ? (64 / NT) : 1;
+  TCFD_HD static int tq(int T) { return (T + 3) / 4; }
+  TCFD_HD static size_t a16(size_t b) { return (b + 15) / 16 * 16; }
+  TCFD_HD static size_t tile_bytes(int T) { return a16((size_t)Y * T * 4); }
+  TCFD_HD static size_t zin_bytes(int my, int mt) { return a16((size_t)2 * my * mt * 8); }
+  // group: tile | exchange | E/Dh | Xy/D | zin (inverse only) | barrier
+  TCFD_HD static size_t group_bytes(int T, int my, int mt, bool inv) {
+    size_t b = tile_bytes(T) + (size_t)Y * 16 + (size_t)(2 * my + 1) * 16 + (size_t)(2 * my) * tq(T) * 4 * 8;
+    if (inv) b += zin_bytes(my, mt);
+    return a16(b + 16);
+  }
+  TCFD_HD static size_t table_bytes(int T, int mt) { return a16((size_t)T * mt * 8); }
+};
+
+template <int Y>
+__global__ void __launch_bounds__(Planes2Smem<Y>::GP * (Y / 8))
+sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1, const cx<float>* __restrict__ A,
+                         const cx<float>* __restrict__ twtab, SconvDims d, int nplanes) {
+  typedef Planes2Smem<Y> S;
+  constexpr int NT = S::NT, GP = S::GP;
+  const int T = d.Tin, my = d.my, mt = d.mt, NKY = 2 * my, TQ = S::tq(T);
+  TCFD_DYN_SMEM(smem_raw);
+  const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+  cx<float>* As = reinterpret_cast<cx<float>*>(smem_raw);  // [mt][T], CTA-shared
+  unsigned char* base = smem_raw + S::table_bytes(T, mt) + (size_t)g * S::group_bytes(T, my, mt, false);
+  const size_t TB = S::tile_bytes(T);
+  const float* tile = reinterpret_cast<const float*>(base);
+  cx<f2>* buf = reinterpret_cast<cx<f2>*>(base + TB);
+  cx<f2>* Es = buf + Y;
+  cx<float>* Xy = reinterpret_cast<cx<float>*>(Es + (2 * my + 1));  // [NKY][TQ*4]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(Xy + (size_t)NKY * TQ * 4);
+  FftTwiddles<float, Y> tw;
+  tw.load(twtab, t);
+  GroupSync<NT> sync{1 + g};
+  int parity = 0;
+  for (int i = threadIdx.x; i < mt * T; i += blockDim.x) As[i] = A[i];
+  const int stride = (int)gridDim.x * GP;
+  const int iters = (nplanes + stride - 1) / stride;
+  auto plane_of = [&](int it) { return (it * (int)gridDim.x + (int)blockIdx.x) * GP + g; };
+  auto issue = [&](int it) {  // one thread of the group
+    int pl = plane_of(it);
+    if (pl >= nplanes) pl = nplanes - 1;
+    stage_expect(bar, (unsigned)((size_t)Y * T * 4));
+    bulk_load(base, x + (size_t)pl * Y * T, (unsigned)((size_t)Y * T * 4), bar);
+  };
+  if (t == 0) stage_barrier_init(bar);
+  __syncthreads();  // tables and barriers visible
+  if (t == 0 && iters > 0) issue(0);
+
+  for (int it = 0; it < iters; ++it) {
+    const int plane = plane_of(it);
+    const bool valid = plane < nplanes;
+    tile_load_wait(bar, (unsigned)(it & 1));
+    for (int q = 0; q < TQ; ++q) {
+      cx<f2> z[1][8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const float* r = tile + (t + m * NT) * T + 4 * q;
+        const float v0 = r[0], v1 = (4 * q + 1 < T) ? r[1] : 0.f, v2 = (4 * q + 2 < T) ? r[2] : 0.f,
+                    v3 = (4 * q + 3 < T) ? r[3] : 0.f;
+        z[0][m] = cx<f2>{f2(v0, v2), f2(v1, v3)};  // lane lo: x[t0] + i x[t0+1]; lane hi: x[t0+2] + i x[t0+3]
+      }
+      if (q == TQ - 1) {
+        // the plane is in registers: the next one is staged under the rest of this plane's work
+        sync();
+        if (t == 0 && it + 1 < iters) issue(it + 1);
+      }
+      fft_run<f2, Y, -1, 1, false, Y>(z, tw, buf, parity, t, sync);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int ky = t + m * NT;
+        if (ky <= my) Es[ky] = z[0][m];
+        else if (ky >= Y - my) Es[my + 1 + ky - (Y - my)] = z[0][m];
+      }
+      sync();
+      for (int kyi = t; kyi < NKY; kyi += NT) {
+        const int ky = kept_freq(kyi, Y, my), kn = (Y - ky) % Y;
+        const cx<f2> e = Es[ky <= my ? ky : my + 1 + ky - (Y - my)];
+        const cx<f2> n = Es[kn <= my ? kn : my + 1 + kn - (Y - my)];
+        const f2 ar = 0.5f * (e.x + n.x), ai = 0.5f * (e.y - n.y);
+        const f2 br = 0.5f * (e.y + n.y), bi = 0.5f * (n.x - e.x);
+        cx<float>* o = Xy + (size_t)kyi * TQ * 4 + 4 * q;
+        o[0] = cx<float>{ar.lo, ai.lo};
+        o[1] = cx<float>{br.lo, bi.lo};
+        o[2] = cx<float>{ar.hi, ai.hi};
+        o[3] = cx<float>{br.hi, bi.hi};
+      }
+      sync();
+    }
+    if (valid) {
+      cx<float>* dst = Z1 + (size_t)plane * NKY * mt;
+      for (int j = t; j < NKY * mt; j += NT) {
+        const int kyi = j / mt, kt = j % mt;
+        const cx<float>* xr = Xy + (size_t)kyi * TQ * 4;
+        const cx<float>* ar = As + (size_t)kt * T;
+        float sr = 0.f, si = 0.f;
+        for (int tt = 0; tt < T; ++tt) {
+          const cx<float> a = ar[tt], v = xr[tt];
+          sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
+          si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
+        }
+        dst[j] = cx<float>{sr, si};
+      }
+    }
+    sync();  // Xy / Es are re-used by the next plane
+  }
+}
+
+template <int Y>
+__global__ void __launch_bounds__(Planes2Smem<Y>::GP * (Y / 8))
+sconv_planes_inv2_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y, const cx<float>* __restrict__ Sy,
+                         const cx<float>* __restrict__ twtab, SconvDims d, int nplanes) {
+  typedef Planes2Smem<Y> S;
+  constexpr int NT = S::NT, GP = S::GP;
+  const int T = d.Tout, my = d.my, mt = d.mt, NKY = 2 * my, TQ = S::tq(T);
+  TCFD_DYN_SMEM(smem_raw);
+  const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+  cx<float>* Ss = reinterpret_cast<cx<float>*>(smem_raw);  // [T][mt], CTA-shared
+  unsigned char* base = smem_raw + S::table_bytes(T, mt) + (size_t)g * S::group_bytes(T, my, mt, true);
+  const size_t TB = S::tile_bytes(T), ZB = S::zin_bytes(my, mt);
+  float* tile = reinterpret_cast<float*>(base);
+  cx<f2>* buf = reinterpret_cast<cx<f2>*>(base + TB);
+  cx<f2>* Dh = buf + Y;
+  cx<float>* D = reinterpret_cast<cx<float>*>(Dh + (2 * my + 1));  // [NKY][TQ*4]
+  unsigned char* zin = reinterpret_cast<unsigned char*>(D + (size_t)NKY * TQ * 4);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(zin + ZB);
+  FftTwiddles<float, Y> tw;
+  tw.load(twtab, t);
+  GroupSync<NT> sync{1 + g};
+  int parity = 0;
+  for (int i = threadIdx.x; i < mt * T; i += blockDim.x) Ss[i] = Sy[i];
+  const int stride = (int)gridDim.x * GP;
+  const int iters = (nplanes + stride - 1) / stride;
+  auto plane_of = [&](int it) { return (it * (int)gridDim.x + (int)blockIdx.x) * GP + g; };
+  auto issue = [&](int it) {  // one thread of the group
+    int pl = plane_of(it);
+    if (pl >= nplanes) pl = nplanes - 1;
+    stage_expect(bar, (unsigned)((size_t)NKY * mt * 8));
+    bulk_load(zin, Z2 + (size_t)pl * NKY * mt, (unsigned)((size_t)NKY * mt * 8), bar);
+  };
+  if (t == 0) stage_barrier_init(bar);
+  __syncthreads();
+  if (t == 0 && iters > 0) issue(0);
+
+  for (int it = 0; it < iters; ++it) {
+    const int plane = plane_of(it);
+    const bool valid = plane < nplanes;
+    tile_load_wait(bar, (unsigned)(it & 1));
+    // t-axis synthesis on the kept ky:  D[kyi][t] = sum_kt Sy[t][kt] Z2[kyi][kt]   (complex)
+    const cx<float>* src = reinterpret_cast<const cx<float>*>(zin);
+    for (int j = t; j < NKY * TQ * 4; j += NT) {
+      const int kyi = j / (TQ * 4), tt = j % (TQ * 4);
+      float sr = 0.f, si = 0.f;
+      if (tt < T) {
+        const cx<float>* zr = src + (size_t)kyi * mt;
+        const cx<float>* sy = Ss + (size_t)tt * mt;
+        for (int kt = 0; kt < mt; ++kt) {
+          const cx<float> a = sy[kt], v = zr[kt];
+          sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
+          si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
+        }
+      }
+      D[j] = cx<float>{sr, si};
+    }
+    sync();  // D complete, zin consumed
+    if (t == 0) {
+      if (it + 1 < iters) issue(it + 1);  // the next block is staged under this plane's transforms
+      bulk_store_wait_read<0>();          // the previous plane's store has read the tile (thread 0 joins the next
+                                          // group barrier only after this, and the tile is first written after it)
+    }
+    for (int q = 0; q < TQ; ++q) {
+      for (int e = t; e < 2 * my + 1; e += NT) {
+        const int ky = e <= my ? e : Y - my + (e - my - 1);
+        const int kn = (Y - ky) % Y;
+        const int i1 = kept_index(ky, Y, my), i2 = kept_index(kn, Y, my);
+        cx<float> h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const cx<float> a = i1 >= 0 ? D[(size_t)i1 * TQ * 4 + 4 * q + j] : cx<float>{0.f, 0.f};
+          const cx<float> b = i2 >= 0 ? D[(size_t)i2 * TQ * 4 + 4 * q + j] : cx<float>{0.f, 0.f};
+          h[j] = cx<float>{0.5f * (a.x + b.x), 0.5f * (a.y - b.y)};
+        }
+        Dh[e] = cx<f2>{f2(h[0].x - h[1].y, h[2].x - h[3].y), f2(h[0].y + h[1].x, h[2].y + h[3].x)};
+      }
+      sync();
+      cx<f2> z[1][8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int ky = t + m * NT;
+        const cx<f2> zero{f2(0.f), f2(0.f)};
+        z[0][m] = ky <= my ? Dh[ky] : (ky >= Y - my ? Dh[my + 1 + ky - (Y - my)] : zero);
+      }
+      fft_run<f2, Y, +1, 1, false, Y>(z, tw, buf, parity, t, sync);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        float* r = tile + (t + m * NT) * T + 4 * q;
+        r[0] = z[0][m].x.lo;
+        if (4 * q + 1 < T) r[1] = z[0][m].y.lo;
+        if (4 * q + 2 < T) r[2] = z[0][m].x.hi;
+        if (4 * q + 3 < T) r[3] = z[0][m].y.hi;
+      }
+      sync();
+    }
+    fence_async_smem();  // this thread's tile writes -> visible to the bulk store
+    sync();
+    if (valid && t == 0) bulk_store(y + (size_t)plane * Y * T, tile, (unsigned)((size_t)Y * T * 4));
+  }
+  if (t == 0) bulk_store_wait_read<0>();  // shared memory must outlive the reads of the last store
+}
+
+// ------------------------------------------------------------------------------------------
 // x-axis transforms on column pairs.  In: FWD  Z [bc][X][ncol]  ->  Xh [bc][2mx][ncol] (kept kx)
 //                                      INV  Yh [bc][2mx][ncol] ->  Z  [bc][X][ncol]  (zero padded)
 // CTA = GP groups of NT = X/8 threads; group g transforms column pair (blockIdx.x * GP + g) of slab
@@ -331,58 +568,83 @@ TCFD_D cx<float> cmul_conj(cx<float> a, cx<float> b) {  // a * conj(b)
 
 constexpr int MIX_BT = 8;  // batch tile held in registers
 
-// Yh[b][o][k] = sum_i Xh[b][i][k] W[i][o][k] (+ delta bias[k]); thread = (k, o), loop over b tiles
+constexpr int MIX_OT = 4;  // output (forward) / input (backward) channels per thread
+
+// Yh[b][o][k] = sum_i Xh[b][i][k] W[i][o][k] (+ delta bias[k]); thread = (k, tile of MIX_OT channels o),
+// loop over b tiles: an Xh entry is read Co / MIX_OT times instead of Co times
 __global__ void __launch_bounds__(128)
 sconv_mix_fwd_kernel(const cx<float>* __restrict__ Xh, cx<float>* __restrict__ Yh, MixArgs a, SconvDims d) {
   const int K = 4 * d.mx * d.my * d.mt, msz = d.mx * d.my * d.mt;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x, o = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, o0 = blockIdx.y * MIX_OT;
   if (k >= K) return;
   int corner, widx;
   mode_split(k, d, corner, widx);
-  const cx<float>* w = a.w[corner] + (size_t)o * msz + widx;
+  const cx<float>* w = a.w[corner] + widx;
   cx<float> bias{0.f, 0.f};
   if (a.bias[corner]) {
     const cx<float> bb = a.bias[corner][widx];
     bias = cx<float>{a.delta * bb.x, a.delta * bb.y};
   }
   for (int b0 = 0; b0 < a.B; b0 += MIX_BT) {
-    cx<float> acc[MIX_BT];
+    cx<float> acc[MIX_BT][MIX_OT];
 #pragma unroll
-    for (int j = 0; j < MIX_BT; ++j) acc[j] = cx<float>{0.f, 0.f};
+    for (int j = 0; j < MIX_BT; ++j)
+#pragma unroll
+      for (int q = 0; q < MIX_OT; ++q) acc[j][q] = cx<float>{0.f, 0.f};
     for (int i = 0; i < a.Ci; ++i) {
-      const cx<float> wi = w[(size_t)i * a.Co * msz];
+      cx<float> wi[MIX_OT], xv[MIX_BT];
+#pragma unroll
+      for (int q = 0; q < MIX_OT; ++q)
+        wi[q] = (o0 + q < a.Co) ? w[((size_t)i * a.Co + o0 + q) * msz] : cx<float>{0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < MIX_BT; ++j)
-        if (b0 + j < a.B) acc[j] = acc[j] + cmul(Xh[((size_t)(b0 + j) * a.Ci + i) * K + k], wi);
+        xv[j] = (b0 + j < a.B) ? Xh[((size_t)(b0 + j) * a.Ci + i) * K + k] : cx<float>{0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < MIX_BT; ++j)
+#pragma unroll
+        for (int q = 0; q < MIX_OT; ++q) acc[j][q] = acc[j][q] + cmul(xv[j], wi[q]);
     }
 #pragma unroll
     for (int j = 0; j < MIX_BT; ++j)
-      if (b0 + j < a.B) Yh[((size_t)(b0 + j) * a.Co + o) * K + k] = acc[j] + bias;
+#pragma unroll
+      for (int q = 0; q < MIX_OT; ++q)
+        if (b0 + j < a.B && o0 + q < a.Co) Yh[((size_t)(b0 + j) * a.Co + o0 + q) * K + k] = acc[j][q] + bias;
   }
 }
 
-// gXh[b][i][k] = sum_o gYh[b][o][k] conj(W[i][o][k]); thread = (k, i)
+// gXh[b][i][k] = sum_o gYh[b][o][k] conj(W[i][o][k]); thread = (k, tile of MIX_OT channels i)
 __global__ void __launch_bounds__(128)
 sconv_mix_bwd_x_kernel(const cx<float>* __restrict__ gYh, cx<float>* __restrict__ gXh, MixArgs a, SconvDims d) {
   const int K = 4 * d.mx * d.my * d.mt, msz = d.mx * d.my * d.mt;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, i0 = blockIdx.y * MIX_OT;
   if (k >= K) return;
   int corner, widx;
   mode_split(k, d, corner, widx);
-  const cx<float>* w = a.w[corner] + (size_t)i * a.Co * msz + widx;
+  const cx<float>* w = a.w[corner] + widx;
   for (int b0 = 0; b0 < a.B; b0 += MIX_BT) {
-    cx<float> acc[MIX_BT];
+    cx<float> acc[MIX_BT][MIX_OT];
 #pragma unroll
-    for (int j = 0; j < MIX_BT; ++j) acc[j] = cx<float>{0.f, 0.f};
+    for (int j = 0; j < MIX_BT; ++j)
+#pragma unroll
+      for (int q = 0; q < MIX_OT; ++q) acc[j][q] = cx<float>{0.f, 0.f};
     for (int o = 0; o < a.Co; ++o) {
-      const cx<float> wo = w[(size_t)o * msz];
+      cx<float> wo[MIX_OT], gv[MIX_BT];
+#pragma unroll
+      for (int q = 0; q < MIX_OT; ++q)
+        wo[q] = (i0 + q < a.Ci) ? w[((size_t)(i0 + q) * a.Co + o) * msz] : cx<float>{0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < MIX_BT; ++j)
-        if (b0 + j < a.B) acc[j] = acc[j] + cmul_conj(gYh[((size_t)(b0 + j) * a.Co + o) * K + k], wo);
+        gv[j] = (b0 + j < a.B) ? gYh[((size_t)(b0 + j) * a.Co + o) * K + k] : cx<float>{0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < MIX_BT; ++j)
+#pragma unroll
+        for (int q = 0; q < MIX_OT; ++q) acc[j][q] = acc[j][q] + cmul_conj(gv[j], wo[q]);
     }
 #pragma unroll
     for (int j = 0; j < MIX_BT; ++j)
-      if (b0 + j < a.B) gXh[((size_t)(b0 + j) * a.Ci + i) * K + k] = acc[j];
+#pragma unroll
+      for (int q = 0; q < MIX_OT; ++q)
+        if (b0 + j < a.B && i0 + q < a.Ci) gXh[((size_t)(b0 + j) * a.Ci + i0 + q) * K + k] = acc[j][q];
   }
 }
 

@@ -118,6 +118,30 @@ TCFD_D void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long 
   std::memcpy(dst, src, bytes);
 #endif
 }
+// 1-D bulk copy shared -> global (SASS: UBLKCP ... bulk_group), committed as one group.  The writers
+// of the shared source must have executed fence_async_smem() and synchronised with the issuing thread.
+TCFD_D void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+#ifndef TCFD_EMU
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<unsigned long long>(gdst)), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#else
+  std::memcpy(gdst, ssrc, bytes);
+#endif
+}
+// wait until at most PENDING of this thread's bulk-store groups are still READING their source
+template <int PENDING>
+TCFD_D void bulk_store_wait_read() {
+#ifndef TCFD_EMU
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+TCFD_D void fence_async_smem() {  // generic-proxy writes to shared memory -> visible to the async proxy
+#ifndef TCFD_EMU
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 TCFD_D void stage_expect(unsigned long long* bar, unsigned bytes) {
 #ifndef TCFD_EMU
   mbar_expect_tx(bar, bytes);
