@@ -401,6 +401,39 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
               else { cc[0][m].x.hi = adv0; cc[0][m].y.hi = adv1; }
             }
           }
+        } else if constexpr ((MODE & 32) != 0) {
+          // the four columns share ONE copy of the unpack + transform code (smaller instruction footprint)
+#pragma unroll 1
+          for (int cidx = 0; cidx < 4; ++cidx) {
+            cx<L> z[1][8];
+  #pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const int k = t + m * NT;
+              const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
+              const int row = lo ? k : N - k;
+              const cx<L> A = tile_ld<T, G>(tile, row, 0, cidx);
+              const cx<L> Bv = tile_ld<T, G>(tile, row, 1, cidx);
+              z[0][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
+              if ((m == 0 || m == 4) && t == 0) z[0][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
+              if constexpr ((MODE & 8) != 0) z[0][m] = (m & 1) ? A : Bv;  // timing experiment: no unpack math
+            }
+            FLOW_FFT(+1, z);
+            if (cidx == 3) {
+              // every thread has passed a barrier after its last tile read: the tile is free
+              if (t == 0) {
+                if (g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
+                else try_stage_next(false);
+              }
+            }
+  #pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const T adv = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
+              if (cidx == 0) cc[0][m].x.lo = adv;
+              if (cidx == 1) cc[0][m].y.lo = adv;
+              if (cidx == 2) cc[0][m].x.hi = adv;
+              if (cidx == 3) cc[0][m].y.hi = adv;
+            }
+          }
         } else {
 #pragma unroll
           for (int cidx = 0; cidx < 4; ++cidx) {

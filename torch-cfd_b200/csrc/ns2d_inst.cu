@@ -249,6 +249,7 @@ int launch_flow(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms,
   TCFD_FLOW_CASE(2, 2, MR)
   if (gr == 3 && gc == 4 && mr == -4) return launch_flow_g<3, 4, MR, 1>(fp, maps, num_sms, stream, win);  // no-FFT timing
   if (gr == 1 && gc == 1 && mr == -4) return launch_flow_g<1, 1, MR, 1>(fp, maps, num_sms, stream, win);
+  if (gr == 3 && gc == 4 && mr == 32) return launch_flow_g<3, 4, MR, 32>(fp, maps, num_sms, stream, win);  // rolled column loop
   // two inverse transforms per thread (V = 2)
   if (gr == 3 && gc == 4 && mr == 2) return launch_flow_g<3, 4, MR, 2>(fp, maps, num_sms, stream, win);
   if (gr == 1 && gc == 1 && mr == 2) return launch_flow_g<1, 1, MR, 2>(fp, maps, num_sms, stream, win);

@@ -247,16 +247,22 @@ struct Planes2Smem {
   // two groups per CTA (at least one warp): shared memory, not the CTA shape, bounds the residency
   static constexpr int GP = (64 / NT) > 0 ? (64 / NT) : 1;
   TCFD_HD static int tq(int T) { return (T + 3) / 4; }
+  // padded row strides (complex entries): an odd stride spreads a column walk over all banks
+  TCFD_HD static int xs(int T) { return tq(T) * 4 + 1; }
+  TCFD_HD static int ts(int n) { return n | 1; }
   TCFD_HD static size_t a16(size_t b) { return (b + 15) / 16 * 16; }
   TCFD_HD static size_t tile_bytes(int T) { return a16((size_t)Y * T * 4); }
   TCFD_HD static size_t zin_bytes(int my, int mt) { return a16((size_t)2 * my * mt * 8); }
   // group: tile | exchange | E/Dh | Xy/D | zin (inverse only) | barrier
   TCFD_HD static size_t group_bytes(int T, int my, int mt, bool inv) {
-    size_t b = tile_bytes(T) + (size_t)Y * 16 + (size_t)(2 * my + 1) * 16 + (size_t)(2 * my) * tq(T) * 4 * 8;
+    size_t b = tile_bytes(T) + (size_t)Y * 16 + (size_t)(2 * my + 1) * 16 + (size_t)(2 * my) * xs(T) * 8;
     if (inv) b += zin_bytes(my, mt);
     return a16(b + 16);
   }
-  TCFD_HD static size_t table_bytes(int T, int mt) { return a16((size_t)T * mt * 8); }
+  TCFD_HD static size_t table_bytes(int T, int mt) {  // [mt][ts(T)] (analysis) or [T][ts(mt)] (synthesis)
+    const int a = T * ts(mt), b = mt * ts(T);
+    return a16((size_t)(a > b ? a : b) * 8);
+  }
 };
 
 template <int Y>
@@ -265,7 +271,7 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
                          const cx<float>* __restrict__ twtab, SconvDims d, int nplanes) {
   typedef Planes2Smem<Y> S;
   constexpr int NT = S::NT, GP = S::GP;
-  const int T = d.Tin, my = d.my, mt = d.mt, NKY = 2 * my, TQ = S::tq(T);
+  const int T = d.Tin, my = d.my, mt = d.mt, NKY = 2 * my, TQ = S::tq(T), XS = S::xs(T), AS = S::ts(T);
   TCFD_DYN_SMEM(smem_raw);
   const int g = threadIdx.x / NT, t = threadIdx.x % NT;
   cx<float>* As = reinterpret_cast<cx<float>*>(smem_raw);  // [mt][T], CTA-shared
@@ -274,13 +280,14 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
   const float* tile = reinterpret_cast<const float*>(base);
   cx<f2>* buf = reinterpret_cast<cx<f2>*>(base + TB);
   cx<f2>* Es = buf + Y;
-  cx<float>* Xy = reinterpret_cast<cx<float>*>(Es + (2 * my + 1));  // [NKY][TQ*4]
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(Xy + (size_t)NKY * TQ * 4);
+  cx<float>* Xy = reinterpret_cast<cx<float>*>(Es + (2 * my + 1));  // [NKY][XS]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(Xy) + S::a16((size_t)NKY * XS * 8));
   FftTwiddles<float, Y> tw;
   tw.load(twtab, t);
   GroupSync<NT> sync{1 + g};
   int parity = 0;
-  for (int i = threadIdx.x; i < mt * T; i += blockDim.x) As[i] = A[i];
+  const bool teven = (T & 1) == 0;
+  for (int i = threadIdx.x; i < mt * T; i += blockDim.x) As[(i / T) * AS + i % T] = A[i];
   const int stride = (int)gridDim.x * GP;
   const int iters = (nplanes + stride - 1) / stride;
   auto plane_of = [&](int it) { return (it * (int)gridDim.x + (int)blockIdx.x) * GP + g; };
@@ -303,8 +310,20 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
         const float* r = tile + (t + m * NT) * T + 4 * q;
-        const float v0 = r[0], v1 = (4 * q + 1 < T) ? r[1] : 0.f, v2 = (4 * q + 2 < T) ? r[2] : 0.f,
-                    v3 = (4 * q + 3 < T) ? r[3] : 0.f;
+        float v0, v1, v2 = 0.f, v3 = 0.f;
+        if (teven) {  // even T: rows and quads are 8-byte aligned
+          const cx<float> p0 = *reinterpret_cast<const cx<float>*>(r);
+          v0 = p0.x; v1 = p0.y;
+          if (4 * q + 2 < T) {
+            const cx<float> p1 = *reinterpret_cast<const cx<float>*>(r + 2);
+            v2 = p1.x; v3 = p1.y;
+          }
+        } else {
+          v0 = r[0];
+          v1 = (4 * q + 1 < T) ? r[1] : 0.f;
+          v2 = (4 * q + 2 < T) ? r[2] : 0.f;
+          v3 = (4 * q + 3 < T) ? r[3] : 0.f;
+        }
         z[0][m] = cx<f2>{f2(v0, v2), f2(v1, v3)};  // lane lo: x[t0] + i x[t0+1]; lane hi: x[t0+2] + i x[t0+3]
       }
       if (q == TQ - 1) {
@@ -326,7 +345,7 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
         const cx<f2> n = Es[kn <= my ? kn : my + 1 + kn - (Y - my)];
         const f2 ar = 0.5f * (e.x + n.x), ai = 0.5f * (e.y - n.y);
         const f2 br = 0.5f * (e.y + n.y), bi = 0.5f * (n.x - e.x);
-        cx<float>* o = Xy + (size_t)kyi * TQ * 4 + 4 * q;
+        cx<float>* o = Xy + (size_t)kyi * XS + 4 * q;
         o[0] = cx<float>{ar.lo, ai.lo};
         o[1] = cx<float>{br.lo, bi.lo};
         o[2] = cx<float>{ar.hi, ai.hi};
@@ -338,8 +357,8 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
       cx<float>* dst = Z1 + (size_t)plane * NKY * mt;
       for (int j = t; j < NKY * mt; j += NT) {
         const int kyi = j / mt, kt = j % mt;
-        const cx<float>* xr = Xy + (size_t)kyi * TQ * 4;
-        const cx<float>* ar = As + (size_t)kt * T;
+        const cx<float>* xr = Xy + (size_t)kyi * XS;
+        const cx<float>* ar = As + (size_t)kt * AS;
         float sr = 0.f, si = 0.f;
         for (int tt = 0; tt < T; ++tt) {
           const cx<float> a = ar[tt], v = xr[tt];
@@ -359,7 +378,7 @@ sconv_planes_inv2_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
                          const cx<float>* __restrict__ twtab, SconvDims d, int nplanes) {
   typedef Planes2Smem<Y> S;
   constexpr int NT = S::NT, GP = S::GP;
-  const int T = d.Tout, my = d.my, mt = d.mt, NKY = 2 * my, TQ = S::tq(T);
+  const int T = d.Tout, my = d.my, mt = d.mt, NKY = 2 * my, TQ = S::tq(T), XS = S::xs(T), SS = S::ts(mt);
   TCFD_DYN_SMEM(smem_raw);
   const int g = threadIdx.x / NT, t = threadIdx.x % NT;
   cx<float>* Ss = reinterpret_cast<cx<float>*>(smem_raw);  // [T][mt], CTA-shared
@@ -368,14 +387,15 @@ sconv_planes_inv2_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
   float* tile = reinterpret_cast<float*>(base);
   cx<f2>* buf = reinterpret_cast<cx<f2>*>(base + TB);
   cx<f2>* Dh = buf + Y;
-  cx<float>* D = reinterpret_cast<cx<float>*>(Dh + (2 * my + 1));  // [NKY][TQ*4]
-  unsigned char* zin = reinterpret_cast<unsigned char*>(D + (size_t)NKY * TQ * 4);
+  cx<float>* D = reinterpret_cast<cx<float>*>(Dh + (2 * my + 1));  // [NKY][XS]
+  unsigned char* zin = reinterpret_cast<unsigned char*>(D) + S::a16((size_t)NKY * XS * 8);
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(zin + ZB);
   FftTwiddles<float, Y> tw;
   tw.load(twtab, t);
   GroupSync<NT> sync{1 + g};
   int parity = 0;
-  for (int i = threadIdx.x; i < mt * T; i += blockDim.x) Ss[i] = Sy[i];
+  const bool teven = (T & 1) == 0;
+  for (int i = threadIdx.x; i < mt * T; i += blockDim.x) Ss[(i / mt) * SS + i % mt] = Sy[i];
   const int stride = (int)gridDim.x * GP;
   const int iters = (nplanes + stride - 1) / stride;
   auto plane_of = [&](int it) { return (it * (int)gridDim.x + (int)blockIdx.x) * GP + g; };
@@ -400,14 +420,14 @@ sconv_planes_inv2_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
       float sr = 0.f, si = 0.f;
       if (tt < T) {
         const cx<float>* zr = src + (size_t)kyi * mt;
-        const cx<float>* sy = Ss + (size_t)tt * mt;
+        const cx<float>* sy = Ss + (size_t)tt * SS;
         for (int kt = 0; kt < mt; ++kt) {
           const cx<float> a = sy[kt], v = zr[kt];
           sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
           si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
         }
       }
-      D[j] = cx<float>{sr, si};
+      D[(size_t)kyi * XS + tt] = cx<float>{sr, si};
     }
     sync();  // D complete, zin consumed
     if (t == 0) {
@@ -423,8 +443,8 @@ sconv_planes_inv2_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
         cx<float> h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const cx<float> a = i1 >= 0 ? D[(size_t)i1 * TQ * 4 + 4 * q + j] : cx<float>{0.f, 0.f};
-          const cx<float> b = i2 >= 0 ? D[(size_t)i2 * TQ * 4 + 4 * q + j] : cx<float>{0.f, 0.f};
+          const cx<float> a = i1 >= 0 ? D[(size_t)i1 * XS + 4 * q + j] : cx<float>{0.f, 0.f};
+          const cx<float> b = i2 >= 0 ? D[(size_t)i2 * XS + 4 * q + j] : cx<float>{0.f, 0.f};
           h[j] = cx<float>{0.5f * (a.x + b.x), 0.5f * (a.y - b.y)};
         }
         Dh[e] = cx<f2>{f2(h[0].x - h[1].y, h[2].x - h[3].y), f2(h[0].y + h[1].x, h[2].y + h[3].x)};
@@ -441,10 +461,15 @@ sconv_planes_inv2_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
         float* r = tile + (t + m * NT) * T + 4 * q;
-        r[0] = z[0][m].x.lo;
-        if (4 * q + 1 < T) r[1] = z[0][m].y.lo;
-        if (4 * q + 2 < T) r[2] = z[0][m].x.hi;
-        if (4 * q + 3 < T) r[3] = z[0][m].y.hi;
+        if (teven) {
+          *reinterpret_cast<cx<float>*>(r) = cx<float>{z[0][m].x.lo, z[0][m].y.lo};
+          if (4 * q + 2 < T) *reinterpret_cast<cx<float>*>(r + 2) = cx<float>{z[0][m].x.hi, z[0][m].y.hi};
+        } else {
+          r[0] = z[0][m].x.lo;
+          if (4 * q + 1 < T) r[1] = z[0][m].y.lo;
+          if (4 * q + 2 < T) r[2] = z[0][m].x.hi;
+          if (4 * q + 3 < T) r[3] = z[0][m].y.hi;
+        }
       }
       sync();
     }
