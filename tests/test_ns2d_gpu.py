@@ -260,3 +260,35 @@ def test_flow_schedule_bit_identical_to_two_launch_schedule(n, batch, W, monkeyp
     for k in range(2):
         for i in range(2):
             assert torch.equal(outs["0"][k][i], outs["1"][k][i])
+
+
+@pytest.mark.gpu
+def test_largest_grid_and_batch_beyond_one_window():
+    """Edge sizes of the dataflow schedule: the largest supported grid (2048^2 fp32, one sample, one CTA
+    per SM) against the oracle, and a batch larger than the default 64-sample window (two chunks whose
+    workspaces are re-used) against per-chunk calls: samples are independent, so bit-identical."""
+    dtype = torch.float32
+    with default_dtype(dtype):
+        n = 2048
+        ns = build_module(n, dtype, 1e-3, 0.1, "vorticity")
+        tb = oracle_tables(n, dtype, 1e-3, 0.1, "vorticity")
+        w0 = O.synthetic_vorticity_hat(n, 1, 13, dtype)
+        w, dwdt = ns(w0.to(DEV), 1e-3, steps=1)
+        wr, dr = O.forward(tb, w0, 1e-3, 1)
+        assert rel_l2(w, wr) < 5e-6
+        assert rel_l2(ns.explicit_terms(w0.to(DEV)), O.explicit_terms(tb, w0)) < 5e-6
+        ns.invalidate_plan()
+
+        n, batch = 256, 80
+        ns = build_module(n, dtype, 1e-3, 0.1, "vorticity")
+        base = O.synthetic_vorticity_hat(n, 4, 21, dtype)
+        w0 = torch.stack([base[i % 4] * (1.0 + 0.01 * i) for i in range(batch)]).to(DEV)
+        full, dfull = ns(w0, 1e-3, steps=2)
+        assert ns._plans[0].last_launch_count == 1
+        part, dpart = ns(w0[64:].contiguous(), 1e-3, steps=2)
+        assert torch.equal(full[64:], part) and torch.equal(dfull[64:], dpart)
+        head, _ = ns(w0[:64].contiguous(), 1e-3, steps=2)
+        assert torch.equal(full[:64], head)
+        tb = oracle_tables(n, dtype, 1e-3, 0.1, "vorticity")
+        wr, _ = O.forward(tb, w0[77:78].cpu(), 1e-3, 2)
+        assert rel_l2(full[77:78], wr) < 5e-6

@@ -249,7 +249,8 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
   const int nsub = fp.nsub;
   constexpr int per_pair = IR + IC;  // items of one {cols, rows} pair per sample
   const int nchunks = (p.B + W - 1) / W;
-  const long long per_chunk = (long long)W * (IR + (long long)nsub * per_pair);  // items of a full chunk
+  // items of a full chunk (the host keeps the total below 2^30: 32-bit ticket arithmetic)
+  const int per_chunk = W * (IR + nsub * per_pair);
   const bool want_dwdt = p.dwdt != nullptr;
 
   int next_tk = 0;  // thread 0: the ticket of the next item (requested one item ahead)
@@ -288,10 +289,10 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
     // ---- decode (chunks are equal-sized except the last)
     // ticket -> chunk c, its size Wc, kind, substage j (-1 = prologue), item index u inside the phase
     auto decode = [&](int tkt, int& c_, int& Wc_, bool& rows_, int& j_, int& u_) -> bool {
-      c_ = (int)((long long)tkt / per_chunk);
+      c_ = nchunks == 1 ? (tkt < per_chunk ? 0 : 1) : tkt / per_chunk;
       if (c_ >= nchunks) return false;
       Wc_ = (c_ == nchunks - 1) ? p.B - c_ * W : W;
-      int r = (int)((long long)tkt - (long long)c_ * per_chunk);
+      int r = tkt - c_ * per_chunk;
       if (r >= Wc_ * (IR + nsub * per_pair)) return false;  // past the end (last chunk)
       if (r < Wc_ * IR) {
         rows_ = true; j_ = -1; u_ = r;
