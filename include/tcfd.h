@@ -167,6 +167,27 @@ int tcfd_sconv3d_backward(tcfd_sconv3d_t* h, const void* grad_y, const void* xha
                           void* grad_x, void* const* grad_w, void* const* grad_bias, float delta, int batch,
                           void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * FNO3d layer glue: the pointwise channel mixes around the spectral convolution,
+ * inference only, fp32, tensors (batch, C, X, Y, T) contiguous with npts = X*Y*T points per channel plane.
+ * Weights are in torch's Conv3d layout [Co][Ci] (kernel size 1), biases [Co] or NULL: DEVICE pointers for
+ * tcfd_fno_pointwise_linear and tcfd_fno_project, HOST pointers for tcfd_fno_layer_glue (its three C x C
+ * matrices travel as a kernel parameter, so that the products read them from the constant bank).
+ * Replaces, in FNO3d.forward (fno/fno3d.py:205-236):
+ *   tcfd_fno_pointwise_linear   x = self.p(x)                                   (:214, Conv3d 1x1x1)
+ *   tcfd_fno_layer_glue         x = nonlinear( mlp(conv(x)) + w(x) )            (:223-230; mlp = MLP :119-130:
+ *                               mlp2(gelu(mlp1(.))), nonlinear = GELU (act 1) or Identity (act 0))
+ *   tcfd_fno_project            x = self.q(x)                                   (:235; MLP with Co = 1 and
+ *                               hidden width M, GELU between when act = 1)
+ * ---------------------------------------------------------------------------------------- */
+int tcfd_fno_pointwise_linear(const float* x, float* y, const float* w, const float* bias, int batch, int Ci, int Co,
+                              size_t npts, void* stream);
+int tcfd_fno_layer_glue(const float* conv_out, const float* x, float* y, const float* w1, const float* b1,
+                        const float* w2, const float* b2, const float* ww, const float* bw, int act, int batch, int C,
+                        size_t npts, void* stream);
+int tcfd_fno_project(const float* x, float* y, const float* w1, const float* b1, const float* w2, const float* b2,
+                     int act, int batch, int C, int M, size_t npts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,11 +134,39 @@ def test_fno3d_forward_matches_reference_structure():
     with torch.no_grad():
         y, aux = m(x)
         assert aux is None and y.shape == (2, 128, 128, 10)
-        # same network with the spectral layers evaluated by the oracle on the CPU
-        h = m.p(x)
-        for conv, mlp, w, act in zip(m.spectral_conv, m.mlp, m.w, m.activation):
-            ws = [getattr(conv, f"weights{i}").detach().cpu() for i in range(1, 5)]
-            h1 = SO.spectral_conv3d(h.cpu(), ws, 8, 8, 5).to(DEV)
-            h = act(mlp(h1) + w(h))
-        yr = m.q(h).squeeze(1)
+        # same network on the CPU (the reference's own fp32 path: torch's GPU convolutions default to
+        # TF32 and are NOT the yardstick) with the spectral layers evaluated by the oracle
+        mc = FNO3d(8, 8, 5, 20, input_channel=10).eval()
+        mc.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+        h = mc.p(x.cpu())
+        for conv, mlp, w, act in zip(mc.spectral_conv, mc.mlp, mc.w, mc.activation):
+            ws = [getattr(conv, f"weights{i}").detach() for i in range(1, 5)]
+            h = act(mlp(SO.spectral_conv3d(h, ws, 8, 8, 5)) + w(h))
+        yr = mc.q(h).squeeze(1)
         assert rel_l2(y, yr) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("width,last_act,padding", [(20, False, 0), (10, True, 0), (12, False, 2)])
+def test_fno3d_fused_inference_matches_torch_op_path(width, last_act, padding):
+    """FNO3d forward (fno/fno3d.py:205-236): the inference path with the fused pointwise glue
+    (tcfd_fno_pointwise_linear / layer_glue / project) against the same module evaluated with the
+    reference's torch ops (TF32 off) around the same spectral convolutions."""
+    from torch_cfd_b200.fno import FNO3d
+    torch.manual_seed(0)
+    m = FNO3d(4, 4, 3, width, input_channel=10, last_activation=last_act, padding=padding).to("cuda:0").eval()
+    n = 32 - 2 * padding  # the padded grid must be a power of two for the spectral convolution
+    x = torch.randn(3, 13, n, n, 10, device="cuda:0")
+    with torch.no_grad():
+        y_fused, _ = m(x)
+    assert y_fused.shape == (3, n, n, 10)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False  # exact fp32 torch ops
+    try:
+        with torch.enable_grad():  # the torch-op path (what autograd uses)
+            y_ops, _ = m(x)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    y_ops = y_ops.detach()
+    err = (torch.linalg.norm(y_fused - y_ops) / torch.linalg.norm(y_ops)).item()
+    assert err < 1e-5, err

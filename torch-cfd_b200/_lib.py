@@ -79,6 +79,10 @@ class TcfdLibrary:
         c.tcfd_sconv3d_last_launch_count.argtypes = [vp]
         c.tcfd_sconv3d_forward.argtypes = [vp, vp, pp, pp, ctypes.c_float, vp, vp, ci, vp]
         c.tcfd_sconv3d_backward.argtypes = [vp, vp, vp, pp, vp, pp, pp, ctypes.c_float, ci, vp]
+        sz = ctypes.c_size_t
+        c.tcfd_fno_pointwise_linear.argtypes = [vp, vp, vp, vp, ci, ci, ci, sz, vp]
+        c.tcfd_fno_layer_glue.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, sz, vp]
+        c.tcfd_fno_project.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, sz, vp]
 
     def check(self, rc: int, what: str):
         if rc != 0:
@@ -293,3 +297,75 @@ class SConv3dPlan:
                                               None if gx is None else gx.data_ptr(), _ptr_array(gw),
                                               _ptr_array(gbias), float(delta), gy.shape[0], _stream_handle(gy))
         self.lib.check(rc, "tcfd_sconv3d_backward")
+
+
+# ------------------------------------------------------------------------------------------------
+# FNO3d layer glue (tcfd_fno_*): thin wrappers over raw pointers; every tensor fp32, contiguous, on one
+# device (CUDA for the product library, CPU for the host-emulation build used by the tests)
+def _fno_check(*ts):
+    dev = ts[0].device
+    for t in ts:
+        if t is None:
+            continue
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+            raise ValueError("tcfd_fno_*: expected contiguous float32 tensors on one device")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def fno_pointwise_linear(lib: TcfdLibrary, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+    """y = Conv3d(kernel 1)(x): x (b, Ci, X, Y, T), weight (Co, Ci, 1, 1, 1) or (Co, Ci)."""
+    w = weight.reshape(weight.shape[0], -1).contiguous()
+    _fno_check(x, w, bias)
+    b, Ci = x.shape[:2]
+    Co, npts = w.shape[0], x[0, 0].numel()
+    y = torch.empty((b, Co) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+    lib.check(lib.c.tcfd_fno_pointwise_linear(x.data_ptr(), y.data_ptr(), w.data_ptr(), _ptr(bias), b, Ci, Co, npts,
+                                              _stream_handle(x)), "tcfd_fno_pointwise_linear")
+    return y
+
+
+def fno_glue_host_weights(w1, b1, w2, b2, ww, bw):
+    """The layer's weights as the HOST tensors tcfd_fno_layer_glue takes (they travel as a kernel
+    parameter): one device->host copy, to be cached by the caller while the parameters do not change."""
+    C = w1.shape[0]
+    host = lambda t, shape: None if t is None else t.detach().to("cpu", torch.float32).reshape(shape).contiguous()
+    return (host(w1, (C, C)), host(b1, (C,)), host(w2, (C, C)), host(b2, (C,)), host(ww, (C, C)), host(bw, (C,)))
+
+
+def fno_layer_glue(lib: TcfdLibrary, conv_out: torch.Tensor, x: torch.Tensor, host_weights, act: bool):
+    """y = act( mlp2(gelu(mlp1(conv_out))) + w(x) ), all channel counts equal; host_weights from
+    fno_glue_host_weights()."""
+    C = x.shape[1]
+    _fno_check(conv_out, x)
+    for t in host_weights:
+        if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ValueError("layer glue: weights must be contiguous float32 HOST tensors")
+    if conv_out.shape != x.shape:
+        raise ValueError("layer glue: conv_out and x must have the same shape")
+    w1, b1, w2, b2, ww, bw = host_weights
+    if tuple(w1.shape) != (C, C) or tuple(w2.shape) != (C, C) or tuple(ww.shape) != (C, C):
+        raise ValueError("layer glue: weight matrices must be (C, C)")
+    y = torch.empty_like(x)
+    lib.check(lib.c.tcfd_fno_layer_glue(conv_out.data_ptr(), x.data_ptr(), y.data_ptr(), w1.data_ptr(), _ptr(b1),
+                                        w2.data_ptr(), _ptr(b2), ww.data_ptr(), _ptr(bw), 1 if act else 0,
+                                        x.shape[0], C, x[0, 0].numel(), _stream_handle(x)), "tcfd_fno_layer_glue")
+    return y
+
+
+def fno_project(lib: TcfdLibrary, x: torch.Tensor, w1, b1, w2, b2, act: bool):
+    """y = mlp2(act(mlp1(x))) with one output channel: x (b, C, X, Y, T) -> (b, 1, X, Y, T)."""
+    C = x.shape[1]
+    w1m = w1.reshape(w1.shape[0], C).contiguous()
+    M = w1m.shape[0]
+    w2m = w2.reshape(-1).contiguous()
+    if w2m.numel() != M:
+        raise ValueError("project: mlp2 must have exactly one output channel")
+    _fno_check(x, w1m, w2m, b1, b2)
+    y = torch.empty((x.shape[0], 1) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+    lib.check(lib.c.tcfd_fno_project(x.data_ptr(), y.data_ptr(), w1m.data_ptr(), _ptr(b1), w2m.data_ptr(), _ptr(b2),
+                                     1 if act else 0, x.shape[0], C, M, x[0, 0].numel(), _stream_handle(x)),
+              "tcfd_fno_project")
+    return y
