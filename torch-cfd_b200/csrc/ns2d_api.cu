@@ -357,7 +357,11 @@ int flow_step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int 
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, static_cast<cudaStream_t>(stream)));
   }
-  const int rc = h->entry.launch_flow(&fp, &h->maps, h->num_sms, stream, &h->win);
+  // grouped items (3 double rows / 4 quads per ticket) only when this call brings enough samples to
+  // keep every SM busy with them; small calls (e.g. the sub-batches of tcfd_ns2d_step_host) use single units
+  tcfd_flow_window_t win = h->win;
+  win.grouped = (h->n >= 512 && (batch < h->chunk ? batch : h->chunk) >= 24) ? 1 : 0;
+  const int rc = h->entry.launch_flow(&fp, &h->maps, h->num_sms, stream, &win);
   if (h->timed) {
     CUDA_TRY(cudaEventRecord(e1, static_cast<cudaStream_t>(stream)));
     h->ev.push_back(e0);
