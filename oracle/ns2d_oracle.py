@@ -224,6 +224,33 @@ def forward(tb: NS2DTables, w_hat: torch.Tensor, dt: float, steps: int = 1, coef
     return w_hat, dwdt
 
 
+def imex_step(tb: NS2DTables, u: torch.Tensor, dt: float, order: float = 2, alpha=0.5, beta=0.5) -> torch.Tensor:
+    """One IMEXStepper step (reference: torch_cfd/equations.py:176-229): order 1 / 1.5 -> ``_imex``
+    (:176-193), order 2 -> ``_rk2_crank_nicolson`` (:195-229).  alpha, beta are 0-d tensors of the default
+    dtype upstream (``params``), so they are taken as such here to round identically."""
+    alpha = torch.as_tensor(alpha, dtype=tb.linear_term.dtype)
+    beta = torch.as_tensor(beta, dtype=tb.linear_term.dtype)
+    F = lambda v: explicit_terms(tb, v)
+    G = lambda v: implicit_terms(tb, v)
+    if order in (1, 1.5):
+        g = u + dt * F(u) + (1 - alpha) * dt * G(u)
+        return implicit_solve(tb, g, alpha * dt)
+    g = u + beta * dt * G(u)
+    h = F(u)
+    u = implicit_solve(tb, g + dt * h, beta * dt)
+    h = alpha * F(u) + (1 - alpha) * h
+    return implicit_solve(tb, g + dt * h, beta * dt)
+
+
+def imex_forward(tb: NS2DTables, w_hat: torch.Tensor, dt: float, steps: int = 1, order: float = 2, alpha=0.5,
+                 beta=0.5):
+    """NavierStokes2DSpectral.forward with an IMEXStepper (equations.py:449-463)."""
+    w = w_hat
+    for _ in range(steps):
+        w = imex_step(tb, w, dt, order, alpha, beta)
+    return w, 1 / (steps * dt) * (w - w_hat)
+
+
 def residual(tb: NS2DTables, w_hat, wt_hat):
     """w_t - F(w) - L w: torch_cfd/equations.py:405-411."""
     return wt_hat - explicit_terms(tb, w_hat) - implicit_terms(tb, w_hat)

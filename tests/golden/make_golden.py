@@ -88,6 +88,35 @@ def ns2d_case(name, n, batch, dtype, viscosity, drag, forcing, steps_list, dt=1e
     print(name, {k: getattr(v, "shape", v) for k, v in out.items() if k.startswith("w_")})
 
 
+def imex_case():
+    """IMEXStepper (torch_cfd/equations.py:110-246): forward-backward Euler (order 1, alpha = 1), standard
+    IMEX Crank-Nicolson (order 1.5) and RK2-CN (order 2, Heun and Ralston weights), 64^2 fp64, forced."""
+    torch.set_default_dtype(torch.float64)
+    from torch_cfd.grids import Grid
+    from torch_cfd.equations import NavierStokes2DSpectral, IMEXStepper
+    from torch_cfd.forcings import KolmogorovForcing
+    from torch_cfd.initial_conditions import vorticity_field
+    n, diam, dt = 64, 2 * torch.pi, 1e-3
+    grid = Grid(shape=(n, n), domain=((0, diam), (0, diam)))
+    forcing_fn = KolmogorovForcing(diam=diam, wave_number=1, grid=grid, scale=1, vorticity=True)
+    w0 = torch.stack([vorticity_field(grid, 4, random_state=s).data for s in range(2)])
+    w0_hat = fft.rfft2(w0)
+    out = dict(n=n, dt=dt, viscosity=1e-3, drag=0.1, diam=float(diam), forcing="vorticity", w0_hat=_np(w0_hat))
+    cases = {"o1": dict(order=1, alpha=1.0), "o15": dict(order=1.5), "o2": dict(order=2),
+             "o2r": dict(order=2, alpha=2.0 / 3.0)}
+    with torch.no_grad():
+        for tag, kw in cases.items():
+            ns = NavierStokes2DSpectral(viscosity=1e-3, grid=grid, drag=0.1, smooth=True, forcing_fn=forcing_fn,
+                                        solver=IMEXStepper(**kw))
+            for s in (1, 3):
+                w, dwdt = ns(w0_hat, dt, steps=s)
+                out[f"{tag}_w_{s}"] = _np(w)
+                out[f"{tag}_dwdt_{s}"] = _np(dwdt)
+    np.savez_compressed(os.path.join(HERE, "ns2d_imex.npz"), **out)
+    print("imex", [k for k in out if k.endswith("_w_3")])
+    torch.set_default_dtype(torch.float32)
+
+
 def mask_case():
     torch.set_default_dtype(torch.float32)
     from torch_cfd.grids import Grid
@@ -180,6 +209,9 @@ def sconv_cases(grid32=False):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "imex":  # only tests/golden/ns2d_imex.npz
+        imex_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sconv32":
         sconv_cases(grid32=True)
         sys.exit(0)
@@ -195,5 +227,6 @@ if __name__ == "__main__":
     ns2d_case("ns2d_fp32_n128_nobatch", 128, 1, torch.float32, 1e-3, 0.1, "vorticity", [1, 5],
               traj=(4, 1))
     mask_case()
+    imex_case()
     sconv_cases()
     sconv_cases(grid32=True)

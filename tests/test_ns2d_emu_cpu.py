@@ -93,6 +93,30 @@ def test_emu_flow_schedule_matches_two_launch_schedule(monkeypatch):
     assert rel_l2(res[("1", "2")][0], ref) < 2e-6
 
 
+def test_emu_imex_crank_nicolson_is_one_fused_substage():
+    """IMEXStepper(order=1.5) (torch_cfd/equations.py:176-193) == one sub-stage of the fused step
+    (beta 0, gamma dt = dt, mu = dt/2): kernels against the reference-generated fixture; and the host
+    logic that decides which IMEX settings may take the fused path."""
+    import torch_cfd_b200 as T
+    g = load_golden("ns2d_imex")
+    dtype = torch.float64
+    tb = _golden_tables(g, dtype)
+    w0 = torch.from_numpy(g["w0_hat"])
+    dt = float(g["dt"])
+    with default_dtype(dtype):
+        st = T.IMEXStepper(order=1.5)
+        assert st.fusable(dt) and T.IMEXStepper(order=1).fusable(dt)
+        assert not T.IMEXStepper(order=1, alpha=1.0).fusable(dt) and not T.IMEXStepper(order=2).fusable(dt)
+        beta, gdt, mu = st.substage_scalars(dt)
+    assert (beta, gdt, mu) == ([0.0], [dt], [0.5 * dt])
+    plan = emu_plan(tb, w0.shape[0], dtype)
+    for s in (1, 3):
+        out, dw = torch.empty_like(w0), torch.empty_like(w0)
+        plan.step(w0, out, dw, s, beta, gdt, mu, 1 / (s * dt))
+        assert rel_l2(out, torch.from_numpy(g[f"o15_w_{s}"])) < 1e-12
+        assert rel_l2(dw, torch.from_numpy(g[f"o15_dwdt_{s}"])) < 1e-8
+
+
 def test_emu_batch_smaller_than_plan_and_errors():
     tb = oracle_tables(32, torch.float32)
     plan = emu_plan(tb, 4, torch.float32)

@@ -112,6 +112,54 @@ class RK4CrankNicolsonStepper(nn.Module):
         return u
 
 
+class IMEXStepper(nn.Module):
+    """Implicit-explicit steppers of configurable order (reference: torch_cfd/equations.py:110-246):
+    order 1 / 1.5 -> ``g = u + dt F(u) + (1 - alpha) dt G(u); u = G_inv(g, alpha dt)`` (:176-193),
+    order 2 -> RK2 + Crank-Nicolson (:195-229).  ``params`` holds ``alpha`` and ``beta`` like upstream.
+
+    With ``alpha = 0.5`` the order-1 / 1.5 step is ONE sub-stage of the fused libtcfd step
+    (beta_k = 0, gamma_k dt = dt, mu = dt / 2): it runs as a single launch per call.  Every other
+    setting takes the generic path: the equation's CUDA ``explicit_terms`` plus torch elementwise ops
+    (the equation module must then live on the state's device, as upstream)."""
+
+    def __init__(self, order: float = 2, alpha: float = 0.5, beta: Optional[float] = 0.5,
+                 requires_grad: bool = False, *args, **kwargs):
+        super().__init__()
+        if order not in (1, 1.5, 2):
+            raise ValueError("IMEXStepper: order must be 1, 1.5 or 2")
+        self.order = order
+        params = {"alpha": torch.tensor(alpha), "beta": torch.tensor(beta)}
+        self.params = nn.ParameterDict({k: nn.Parameter(v, requires_grad=requires_grad) for k, v in params.items()})
+        self.requires_grad = requires_grad
+
+    def fusable(self, dt: float, params: Optional[Params] = None) -> bool:
+        """True when the step is one sub-stage of the fused kernel: numerator and denominator of the
+        implicit part use the same factor, (1 - alpha) dt == alpha dt."""
+        params = self.params if params is None else params
+        a = params["alpha"]
+        return self.order in (1, 1.5) and float((1 - a) * dt) == float(a * dt)
+
+    def substage_scalars(self, dt: float, params: Optional[Params] = None):
+        params = self.params if params is None else params
+        return [0.0], [float(dt)], [float(params["alpha"] * dt)]
+
+    def forward(self, u: torch.Tensor, dt: float, equation: ImplicitExplicitODE,
+                params: Optional[Params] = None) -> torch.Tensor:
+        if isinstance(equation, NavierStokes2DSpectral) and self.fusable(dt, params):
+            return equation._fused_steps(u, dt, 1, self, params, want_dudt=False)[0]
+        params = self.params if params is None else params
+        alpha, beta = params["alpha"], params["beta"]
+        F, G, G_inv = equation.explicit_terms, equation.implicit_terms, equation.implicit_solve
+        if self.order in (1, 1.5):
+            g = u + dt * F(u) + (1 - alpha) * dt * G(u)
+            return G_inv(g, alpha * dt)
+        g = u + beta * dt * G(u)
+        h = F(u)
+        u = G_inv(g + dt * h, beta * dt)
+        h = alpha * F(u) + (1 - alpha) * h
+        return G_inv(g + dt * h, beta * dt)
+
+
 def _probe_state_independent(forcing_fn, grid: Grid, vorticity: bool) -> bool:
     n = grid.shape[0]
     g = torch.Generator().manual_seed(0)
@@ -267,6 +315,8 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         """vort_hat: (B, n, n//2+1), (n_t, n, n//2+1) or (n, n//2+1) complex spectrum.
         Returns (vort_hat after ``steps`` steps, (new - old) / (steps * dt))."""
         if isinstance(self.solver, RK4CrankNicolsonStepper):
+            return self._fused_steps(vort_hat, dt, steps, self.solver)
+        if isinstance(self.solver, IMEXStepper) and self.solver.fusable(dt):
             return self._fused_steps(vort_hat, dt, steps, self.solver)
         if self.solver is None:
             raise TypeError("NavierStokes2DSpectral.solver is None: pass solver=RK4CrankNicolsonStepper()")
