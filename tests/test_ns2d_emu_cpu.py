@@ -187,6 +187,25 @@ def test_module_host_logic_matches_reference_tables():
         assert list(brick_wall_bounds(n)) + [int(m.sum())] == gm[f"n{n}"].tolist()
 
 
+def test_stable_time_step_matches_reference_values():
+    """stable_time_step (torch_cfd/equations.py:35-64): same signature / defaults / positional order, and
+    the values the reference returns (computed with the reference itself in the authoring container)."""
+    import inspect
+    import math
+    import torch_cfd_b200 as T
+    sig = [(p.name, p.default) for p in inspect.signature(T.stable_time_step).parameters.values()]
+    assert sig == [("dx", None), ("dt", None), ("max_velocity", 1.0), ("max_courant_number", 0.5),
+                   ("viscosity", 1e-3), ("implicit_diffusion", True), ("ndim", 2)]
+    f = T.stable_time_step
+    assert f(dx=2 * math.pi / 64, dt=1e-3, viscosity=1e-3, max_velocity=7.0) == 0.001          # C1 (SURVEY 8c)
+    assert f(dx=1 / 256, dt=1.0, max_velocity=2.0) == 0.0009765625
+    assert f(dx=0.01) == 0.005
+    assert f(dx=1 / 2048, dt=1e-3, viscosity=1e-3, max_velocity=7.0, implicit_diffusion=False) == 3.487723214285714e-05
+    assert f(dx=0.05, dt=None, max_velocity=3.0, max_courant_number=0.9, viscosity=0.5, implicit_diffusion=False,
+             ndim=3) == 0.0006250000000000001
+    assert f(0.1, 0.2, 4.0) == 0.0125
+
+
 def test_module_refuses_cpu_and_bad_inputs():
     from _common import build_module
     with default_dtype(torch.float32):

@@ -26,15 +26,18 @@ from .spectral import brick_wall_filter_2d, spectral_laplacian_2d
 Params = Dict[str, torch.Tensor]
 
 
-def stable_time_step(dx: float = None, dt: float = None, viscosity: float = None,
-                     max_velocity: float = 2.0, max_courant_number: float = 0.5,
+def stable_time_step(dx: float = None, dt: float = None, max_velocity: float = 1.0,
+                     max_courant_number: float = 0.5, viscosity: float = 1e-3,
                      implicit_diffusion: bool = True, ndim: int = 2) -> float:
-    """Host scalar helper (reference: torch_cfd/equations.py:35-64): the advection CFL bound,
-    tightened by the diffusive bound when diffusion is explicit, never larger than ``dt``."""
-    dt_adv = max_courant_number * dx / max_velocity
+    """Host scalar helper with the reference's signature and defaults (torch_cfd/equations.py:35-64):
+    min(diffusive bound, advective CFL bound, dt); the diffusive bound is ``dx`` when diffusion is
+    implicit and ``dx^2 / (viscosity 2^ndim)`` when it is explicit."""
+    dt_diffusion = dx
     if not implicit_diffusion:
-        dt_adv = min(dt_adv, dx**2 / (viscosity * 2**ndim))
-    return min(dx, dt_adv, dt) if dt is not None else min(dx, dt_adv)
+        dt_diffusion = dx**2 / (viscosity * 2 ** (ndim))
+    dt_advection = max_courant_number * dx / max_velocity
+    dt = dt_advection if dt is None else dt
+    return min(dt_diffusion, dt_advection, dt)
 
 
 class ImplicitExplicitODE(nn.Module):
