@@ -117,6 +117,52 @@ def imex_case():
     torch.set_default_dtype(torch.float32)
 
 
+def signature_case():
+    """Names, defaults and order of the parameters of every reference callable the shims stand in for
+    (the drop-in boundary of SURVEY 8b) -> tests/golden/signatures.json."""
+    import inspect
+    import json
+    import torch_cfd.equations as RE, torch_cfd.grids as RG, torch_cfd.forcings as RF, torch_cfd.spectral as RS
+    import fno.fno3d as F3, fno.sfno as SF
+    sol = load_solvers()
+    targets = {
+        "stable_time_step": RE.stable_time_step,
+        "NavierStokes2DSpectral.__init__": RE.NavierStokes2DSpectral.__init__,
+        "NavierStokes2DSpectral.forward": RE.NavierStokes2DSpectral.forward,
+        "NavierStokes2DSpectral.explicit_terms": RE.NavierStokes2DSpectral.explicit_terms,
+        "NavierStokes2DSpectral.implicit_terms": RE.NavierStokes2DSpectral.implicit_terms,
+        "NavierStokes2DSpectral.implicit_solve": RE.NavierStokes2DSpectral.implicit_solve,
+        "NavierStokes2DSpectral.residual": RE.NavierStokes2DSpectral.residual,
+        "RK4CrankNicolsonStepper.__init__": RE.RK4CrankNicolsonStepper.__init__,
+        "RK4CrankNicolsonStepper.forward": RE.RK4CrankNicolsonStepper.forward,
+        "IMEXStepper.__init__": RE.IMEXStepper.__init__,
+        "IMEXStepper.forward": RE.IMEXStepper.forward,
+        "get_trajectory_imex": sol.get_trajectory_imex,
+        "Grid.__init__": RG.Grid.__init__,
+        "KolmogorovForcing.__init__": RF.KolmogorovForcing.__init__,
+        "brick_wall_filter_2d": RS.brick_wall_filter_2d,
+        "vorticity_to_velocity": RS.vorticity_to_velocity,
+        "fno.SpectralConv3d.__init__": F3.SpectralConv3d.__init__,
+        "fno.SpectralConv3d.forward": F3.SpectralConv3d.forward,
+        "fno.FNO3d.__init__": F3.FNO3d.__init__,
+        "fno.FNO3d.forward": F3.FNO3d.forward,
+        "fno.SpectralConvS.__init__": SF.SpectralConvS.__init__,
+        "fno.SpectralConvT.__init__": SF.SpectralConvT.__init__,
+        "fno.SpectralConvT.forward": SF.SpectralConvT.forward,
+    }
+
+    def enc(d):
+        if d is inspect._empty:
+            return "<required>"
+        return d if isinstance(d, (int, float, bool, str, type(None))) else repr(d)
+
+    out = {k: [[p.name, enc(p.default), p.kind.name] for p in inspect.signature(f).parameters.values()]
+           for k, f in targets.items()}
+    with open(os.path.join(HERE, "signatures.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    print("signatures", len(out))
+
+
 def mask_case():
     torch.set_default_dtype(torch.float32)
     from torch_cfd.grids import Grid
@@ -209,6 +255,9 @@ def sconv_cases(grid32=False):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "signatures":
+        signature_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "imex":  # only tests/golden/ns2d_imex.npz
         imex_case()
         sys.exit(0)
@@ -227,6 +276,7 @@ if __name__ == "__main__":
     ns2d_case("ns2d_fp32_n128_nobatch", 128, 1, torch.float32, 1e-3, 0.1, "vorticity", [1, 5],
               traj=(4, 1))
     mask_case()
+    signature_case()
     imex_case()
     sconv_cases()
     sconv_cases(grid32=True)

@@ -214,3 +214,37 @@ def test_module_refuses_cpu_and_bad_inputs():
             ns(torch.zeros(1, 64, 33, dtype=torch.complex64), 1e-3)
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             ns.explicit_terms(torch.zeros(64, 33, dtype=torch.complex64))
+
+
+def test_drop_in_signatures_match_reference():
+    """every shim takes the reference's parameters -- same names, order, kinds and defaults
+    (tests/golden/signatures.json, written from the reference by make_golden.py); a shim may only APPEND
+    optional parameters."""
+    import inspect
+    import json
+    import torch_cfd_b200 as T
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "signatures.json")))
+
+    def enc(d):
+        if d is inspect._empty:
+            return "<required>"
+        return d if isinstance(d, (int, float, bool, str, type(None))) else repr(d)
+
+    for name, want in ref.items():
+        obj = T
+        for part in name.split("."):
+            obj = getattr(obj, part)
+        got = [[p.name, enc(p.default), p.kind.name] for p in inspect.signature(obj).parameters.values()]
+        var_kw = [g for g in got if g[2] == "VAR_KEYWORD"]
+        core = [g for g in got if g[2] != "VAR_KEYWORD"]
+        want_core = [w for w in want if w[2] != "VAR_KEYWORD"]
+        for w, g in zip(want_core, core):
+            if w[0] == "postprocess":  # upstream default is an nn.Identity() instance; None means the same here
+                assert g[0] == "postprocess"
+                continue
+            assert w == g, (name, w, g)
+        assert len(core) >= len(want_core), name
+        for extra in core[len(want_core):]:
+            assert extra[1] != "<required>", (name, extra)
+        if any(w[2] == "VAR_KEYWORD" for w in want):
+            assert var_kw, name
