@@ -67,6 +67,17 @@ def main():
         else:
             rec["bit_equal_to_first"] = bool(torch.equal(w, ref[0]) and torch.equal(dw, ref[1]))
         rec["finite"] = bool(torch.isfinite(torch.view_as_real(w)).all().item())
+        if os.environ.get("TCFD_FLOW_PROF"):  # region cycle attribution (profiling kernel variant only)
+            import ctypes
+            plan = ns._plans[0]
+            out = (ctypes.c_ulonglong * 16)()
+            fn = plan.lib.c.tcfd_ns2d_flow_profile
+            fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]
+            if fn(plan._h, out) == 0:
+                tot = float(sum(out)) or 1.0
+                names = ["control", "dep_wait", "stage_wait", "fft", "cols_math", "rows_unit_head", "rows_fields", "item_barrier",
+                         "rows_prologue_loads", "rows_update", "rows_post_update"]
+                rec["cycles_share"] = {nm: round(out[i] / tot, 4) for i, nm in enumerate(names)}
         print(json.dumps(rec), flush=True)
         ns.invalidate_plan()
         del ns

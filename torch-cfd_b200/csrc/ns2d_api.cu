@@ -66,6 +66,7 @@ struct tcfd_ns2d {
   int* sync_dev = nullptr;   // ticket + per-sample counters
   int* err_host = nullptr;   // mapped pinned word the kernel raises on a dependency time-out
   int* err_dev = nullptr;
+  unsigned long long* prof_dev = nullptr;  // region cycle counters of the profiling kernel variant (TCFD_FLOW_PROF=1)
   void* slab = nullptr;      // one allocation behind H, advt, wS, hA, wT, hB (dataflow schedule)
   tcfd_flow_window_t win{};  // L2 access-policy window over the hot part of the slab
   // measurement mode (tcfd_ns2d_step_timed): every launch is bracketed by events
@@ -350,6 +351,7 @@ int flow_step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int 
   fp.hU = static_cast<CU*>(h->hA);
   fp.sync = h->sync_dev;
   fp.err = h->err_dev;
+  fp.prof = h->prof_dev;
   CUDA_TRY(cudaMemsetAsync(h->sync_dev, 0, sizeof(int) * (2 + 2 * (size_t)h->max_batch), static_cast<cudaStream_t>(stream)));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timed) {
@@ -461,6 +463,10 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
         rc = fail(TCFD_ERR_NOMEM, "flow schedule: synchronisation block allocation failed");
       else
         *h->err_host = 0;
+      if (rc == 0 && getenv("TCFD_FLOW_PROF") && atoi(getenv("TCFD_FLOW_PROF"))) {
+        if (cudaMalloc(reinterpret_cast<void**>(&h->prof_dev), 16 * sizeof(unsigned long long)) == cudaSuccess)
+          cudaMemset(h->prof_dev, 0, 16 * sizeof(unsigned long long));
+      }
     }
     h->chunk = chunk;
     const size_t sb = h->state_bytes(h->chunk);
@@ -549,6 +555,7 @@ extern "C" int tcfd_ns2d_destroy(tcfd_ns2d_t* h) {
       if (p) cudaFree(p);
   }
   if (h->sync_dev) cudaFree(h->sync_dev);
+  if (h->prof_dev) cudaFree(h->prof_dev);
   if (h->err_host) cudaFreeHost(h->err_host);
   for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
@@ -593,6 +600,16 @@ extern "C" int tcfd_ns2d_check(const tcfd_ns2d_t* h) {
   if (!h) return fail(TCFD_ERR_INVALID, "null handle");
   if (h->err_host && *reinterpret_cast<volatile int*>(h->err_host) != 0)
     return fail(TCFD_ERR_CUDA, "dataflow schedule: a dependency wait timed out in an earlier call; results are invalid");
+  return TCFD_OK;
+}
+
+// experiments only (not declared in tcfd.h): region cycle counters of the profiling kernel variant
+// (-DTCFD_FLOW_VARIANTS build, TCFD_FLOW_PROF=1, TCFD_FLOW_G="3,4,-64"); synchronises the device, reads and clears
+extern "C" int tcfd_ns2d_flow_profile(tcfd_ns2d_t* h, unsigned long long* out16) {
+  if (!h || !out16 || !h->prof_dev) return fail(TCFD_ERR_INVALID, "no profile counters on this handle");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out16, h->prof_dev, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(h->prof_dev, 0, 16 * sizeof(unsigned long long)));
   return TCFD_OK;
 }
 

@@ -44,6 +44,7 @@ struct FlowParams {
   cx<typename pack2<T>::type>* w0U; // [W] unit-layout copy of the call's input state (dw/dt), or null
   int* sync;  // [0] ticket, [1] unused, [2 .. 2+B) rows counters, [2+B .. 2+2B) cols counters
   int* err;   // host-visible error word (0 = ok)
+  unsigned long long* prof;  // [16] cycles of thread 0 per region, summed over CTAs (profiling variant only)
 };
 
 // ------------------------------------------------------------------------------------------ sync
@@ -125,6 +126,13 @@ TCFD_D void flow_st_stream(cx<T>* p, cx<T> v) {
   *p = v;
 #endif
 }
+TCFD_D long long flow_clock() {
+#ifndef TCFD_EMU
+  return clock64();
+#else
+  return 0;
+#endif
+}
 TCFD_D void flow_proxy_fence() {
 #ifndef TCFD_EMU
   asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -189,10 +197,42 @@ TCFD_D cx<typename lane_traits<L>::scalar> lane_rt(cx<L> v, int lane) {
 // ------------------------------------------------------------------------------------------ kernel
 // Timing experiment (-DTCFD_FLOW_VARIANTS builds, MODE 1): the transforms are replaced by one barrier, so
 // the launch measures everything BUT the FFTs (results are meaningless).
+// MODE bit 6: thread 0 of every CTA attributes its cycles (clock64) to regions -- 0 control (ticket, decode,
+// release), 1 dependency wait, 2 staging wait (mbarrier), 3 transforms, 4 cols arithmetic + stores, 5 rows
+// unit head (scalars, advection row), 6 rows spectral fields + H stores, 7 end-of-item barrier, 8 rows prologue
+// loads, 9 rows RK/CN update proper, 10 rows post-update barrier + staging of the next unit -- summed into fp.prof.
+#define FLOW_MARK(R)                                                       \
+  do {                                                                     \
+    if constexpr ((MODE & 64) != 0) {                                      \
+      if (ctl) {                                                        \
+        const long long now_ = flow_clock();                               \
+        prof_acc[prof_cur] += now_ - prof_last;                            \
+        prof_last = now_;                                                  \
+        prof_cur = (R);                                                    \
+      }                                                                    \
+    }                                                                      \
+  } while (0)
 #define FLOW_FFT(DIR, ARR)                                                \
   do {                                                                    \
+    const int pr_ = prof_cur;                                             \
+    FLOW_MARK(3);                                                         \
     if constexpr ((MODE & 1) != 0) __syncthreads();                       \
     else fft_run<L, N, DIR, 1, false, N>(ARR, tw, buf, parity, t, sync);  \
+    FLOW_MARK(pr_);                                                       \
+  } while (0)
+#define FLOW_LOADWAIT(BAR, PH)  \
+  do {                          \
+    const int pr_ = prof_cur;   \
+    FLOW_MARK(2);               \
+    tile_load_wait(BAR, PH);    \
+    FLOW_MARK(pr_);             \
+  } while (0)
+#define FLOW_DEPWAIT(PTR, TGT)        \
+  do {                                \
+    const int pr_ = prof_cur;         \
+    FLOW_MARK(1);                     \
+    flow_wait(PTR, TGT, fp.err);      \
+    FLOW_MARK(pr_);                   \
   } while (0)
 // MODE bit 1: the inverse transforms run two per thread (V = 2: twice the independent work per warp and
 // half the barriers; needs the register budget of 256 resident threads per SM and a 2 N exchange buffer)
@@ -234,6 +274,10 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
   volatile int* sh = reinterpret_cast<volatile int*>(bar_s + 4);                          // [0] ticket
 
   const int t = threadIdx.x;
+  // the CONTROL thread (tickets, dependency polls, staging, release).  (Moving it to the last warp, away from
+  // thread 0's extra self-conjugate entries, was measured 6 % slower: the two single-thread sections sit
+  // between different barriers, so splitting them over the warps only adds waiting.)
+  const bool ctl = t == 0;
   FftTwiddles<T, N> tw;
   tw.load(p.tw, t);
   CtaSync sync;
@@ -253,8 +297,10 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
   const int per_chunk = W * (IR + nsub * per_pair);
   const bool want_dwdt = p.dwdt != nullptr;
 
+  long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, prof_last = flow_clock();  // (profiling variant only)
+  int prof_cur = 0;
   int next_tk = 0;  // thread 0: the ticket of the next item (requested one item ahead)
-  if (t == 0) {
+  if (ctl) {
     stage_barrier_init(bar_s);
     stage_barrier_init(bar_t);
     stage_barrier_init(bar_a);
@@ -278,10 +324,11 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
   for (;;) {
     // here: the previous item is complete (its stores are ordered before the last barrier, shared
     // memory is free) and sh[0] holds this item's ticket
+    FLOW_MARK(0);
     const int tk = sh[it & 1];
     const bool staged = sh[2 + (it & 1)] != 0;  // thread 0 issued this item's first loads during the previous item
     ++it;
-    if (t == 0) {
+    if (ctl) {
       if (pending) flow_signal(pending);
       pending = nullptr;
       next_tk = flow_fetch_add(ticket, 1);  // consumed at the end of this item
@@ -358,17 +405,18 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
 
     if (!is_rows) {
       // ================================================================= cols item: GC quads
+      FLOW_MARK(4);
       const int sl = u / IC, q0 = (u % IC) * GC;  // slot inside the chunk, first quad
       const int s = c * W + sl;
-      if (t == 0 && !staged) {
-        flow_wait(&cnt_rows[s], IR * (j + 1), fp.err);
+      if (ctl && !staged) {
+        FLOW_DEPWAIT(&cnt_rows[s], IR * (j + 1));
         tile_load_issue<NH, IB>(tile, maps, q0 * 4, sl, bar_s);
       }
 #pragma unroll 1
       for (int g = 0; g < GC; ++g) {
         const int y0 = (q0 + g) * 4;
         cx<L> cc[1][8];
-        tile_load_wait(bar_s, phase_s);
+        FLOW_LOADWAIT(bar_s, phase_s);
         phase_s ^= 1u;
         if constexpr (V2) {
 #pragma unroll
@@ -389,7 +437,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
             FLOW_FFT2(+1, z);
             if (pr == 1) {
               // every thread has passed a barrier after its last tile read: the tile is free
-              if (t == 0) {
+              if (ctl) {
                 if (g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
                 else try_stage_next(false);
               }
@@ -421,7 +469,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
             FLOW_FFT(+1, z);
             if (cidx == 3) {
               // every thread has passed a barrier after its last tile read: the tile is free
-              if (t == 0) {
+              if (ctl) {
                 if (g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
                 else try_stage_next(false);
               }
@@ -453,7 +501,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
             FLOW_FFT(+1, z);
             if (cidx == 3) {
               // every thread has passed a barrier after its last tile read: the tile is free
-              if (t == 0) {
+              if (ctl) {
                 if (g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
                 else try_stage_next(false);
               }
@@ -487,16 +535,18 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         }
         if (g + 1 < GC) __syncthreads();  // buf is re-used by the next quad's transforms
       }
-      if (t == 0) {
+      if (ctl) {
         sh[it & 1] = next_tk;
         sh[2 + (it & 1)] = staged_next;
         pending = &cnt_cols[s];
       }
+      FLOW_MARK(7);
       __syncthreads();
       continue;
     }
 
     // =================================================================== rows item: up to GR units
+    FLOW_MARK(5);
     const int sl = u / IR, d0 = (u % IR) * GR;
     const int gn = (ND - d0) < GR ? (ND - d0) : GR;
     const int s = c * W + sl;
@@ -509,17 +559,18 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
     const size_t sb = (size_t)s * N * NH;  // reference layout: sample base
     const T beta = fp.beta[k], gdt = fp.gdt[k], mu = fp.mu[k];
 
-    if (t == 0 && !staged) {
+    if (ctl && !staged) {
       if (prologue) {
-        if (s >= W) flow_wait(&cnt_rows[s - W], IR * (nsub + 1), fp.err);
+        if (s >= W) FLOW_DEPWAIT(&cnt_rows[s - W], IR * (nsub + 1));
       } else {
-        flow_wait(&cnt_cols[s], IC * (j + 1), fp.err);
+        FLOW_DEPWAIT(&cnt_cols[s], IC * (j + 1));
       }
       issue_unit(sl, d0, tabsel, prologue, rd_h);
     }
 
 #pragma unroll 1
     for (int g = 0; g < gn; ++g) {
+      FLOW_MARK(5);
       const int d = d0 + g;
       const size_t ub = ((size_t)sl * ND + d) * 2 * NH;  // unit layout: block base (slot)
       const bool valid1 = 2 * d + 1 <= N / 2;
@@ -534,6 +585,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
 
       cx<L> wv[8], e0, e1;  // e0 = entries (r2, 0), e1 = entries (r1, N/2): owned by thread 0
       if (prologue) {
+        FLOW_MARK(8);
         const cx<T>* w = p.w_in + sb;
         const int lo_a = r1a * NH + t, hi_a = r2a * NH + N - t, lo_b = r1b * NH + t, hi_b = r2b * NH + N - t;
 #pragma unroll
@@ -551,7 +603,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         }
         // the table block was issued by thread 0 AFTER its dependency wait: its arrival also tells
         // every other thread that the slot's previous occupant is done (stores below re-use the slot)
-        tile_load_wait(bar_t, phase_t);
+        FLOW_LOADWAIT(bar_t, phase_t);
         phase_t ^= 1u;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
@@ -571,7 +623,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         const bool forced = p.fhat && (p.frow[r1a] | p.frow[r2a] | p.frow[r1b] | p.frow[r2b]);
         cx<L> a[1][8];
         if (d < p.NDF) {
-          tile_load_wait(bar_a, phase_a);
+          FLOW_LOADWAIT(bar_a, phase_a);
           phase_a ^= 1u;
 #pragma unroll
           for (int m = 0; m < 8; ++m) a[0][m] = advst[t + m * NT];
@@ -584,20 +636,21 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         if (ld_old) {
           // the advection row is in registers (a barrier of the transform lies behind its reads): the
           // ADV stage takes this unit's block of the call's input state
-          if (t == 0) {
+          if (ctl) {
             stage_expect(bar_o, (unsigned)R::UNIT_BYTES);
             bulk_load(area + S::OFF_ADV, fp.w0U + ub, (unsigned)R::UNIT_BYTES, bar_o);
           }
         }
-        tile_load_wait(bar_t, phase_t);
+        FLOW_LOADWAIT(bar_t, phase_t);
         phase_t ^= 1u;
-        tile_load_wait(bar_s, phase_s);
+        FLOW_LOADWAIT(bar_s, phase_s);
         phase_s ^= 1u;
         if (ld_old) {
-          tile_load_wait(bar_o, phase_o);
+          FLOW_LOADWAIT(bar_o, phase_o);
           phase_o ^= 1u;
         }
         // RK / CN update of entry (half, col) in both lanes; returns the new w
+        FLOW_MARK(9);
         auto update = [&](int half, int col, cx<L> A, bool own_a, bool own_b) -> cx<L> {
           if constexpr ((MODE & 16) != 0) {  // timing experiment: loads and stores only
             const cx<L> w_ = wst[half * NH + col];
@@ -620,7 +673,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
           if (rd_h) h = F + L(beta) * hst[half * NH + col];
           if (wr_h) fp.hU[ub + half * NH + col] = h;
           const L den = L(T(1)) - L(mu) * lin;
-          const L inv(rcp_rn(den.lo), rcp_rn(den.hi));
+          const L inv(rcp_cn(den.lo), rcp_cn(den.hi));
           const cx<L> x = (w + L(gdt) * h) + L(mu) * (lin * w);
           const cx<L> wn = inv * x;
           if (last_sub) {
@@ -650,14 +703,16 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
       }
       // the W / H / ADV stages are consumed (and the other table block has been free since the
       // previous unit's inverse transforms): stage the next unit under this unit's inverse transforms
+      FLOW_MARK(10);
       __syncthreads();
-      if (t == 0) {
+      if (ctl) {
         if (g + 1 < gn) issue_unit(sl, d + 1, tabsel ^ 1u, prologue, rd_h);
         else try_stage_next(true);
       }
       tabsel ^= 1u;
 
       if (do_inv) {
+        FLOW_MARK(6);
         const T ky0 = p.kappa_y[0], kyh = p.kappa_y[N / 2];
         if constexpr (V2) {
           // both halves of a lane side by side: (u, dw/dx) -> plane 0, (v, dw/dy) -> plane 1
@@ -735,12 +790,21 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         }
       }
     }
-    if (t == 0) {
+    if (ctl) {
       sh[it & 1] = next_tk;
       sh[2 + (it & 1)] = staged_next;
       pending = &cnt_rows[s];
     }
+    FLOW_MARK(7);
     __syncthreads();
+  }
+  if constexpr ((MODE & 64) != 0) {
+    FLOW_MARK(0);
+    if (ctl && fp.prof) {
+#ifndef TCFD_EMU
+      for (int r = 0; r < 16; ++r) atomicAdd(fp.prof + r, (unsigned long long)prof_acc[r]);
+#endif
+    }
   }
 }
 

@@ -254,6 +254,9 @@ int launch_flow(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms,
   if (gr == 3 && gc == 4 && mr == 2) return launch_flow_g<3, 4, MR, 2>(fp, maps, num_sms, stream, win);
   if (gr == 1 && gc == 1 && mr == 2) return launch_flow_g<1, 1, MR, 2>(fp, maps, num_sms, stream, win);
   if (gr == 3 && gc == 4 && mr == -2) return launch_flow_g<3, 4, MR, 3>(fp, maps, num_sms, stream, win);
+  // cycle attribution per region (fp.prof)
+  if (gr == 3 && gc == 4 && mr == -64) return launch_flow_g<3, 4, MR, 64>(fp, maps, num_sms, stream, win);
+  if (gr == 1 && gc == 1 && mr == -64) return launch_flow_g<1, 1, MR, 64>(fp, maps, num_sms, stream, win);
   // timing experiments on top of the no-FFT twin: -5 no fields, -9 no tile unpack, -17 no update math, -29 all
   if (gr == 3 && gc == 4 && mr == -5) return launch_flow_g<3, 4, MR, 5>(fp, maps, num_sms, stream, win);
   if (gr == 3 && gc == 4 && mr == -9) return launch_flow_g<3, 4, MR, 9>(fp, maps, num_sms, stream, win);

@@ -390,7 +390,7 @@ ns2d_rows3_kernel(const NsParams<T> p) {
       if (p.read_h) h = F + L(p.beta) * hst[half * NH + col];
       if (p.write_h) p.hU_out[ub + half * NH + col] = h;
       const L den = L(T(1)) - L(p.mu) * lin;
-      const L inv(rcp_rn(den.lo), rcp_rn(den.hi));
+      const L inv(rcp_cn(den.lo), rcp_cn(den.hi));
       const cx<L> x = (w + L(p.gdt) * h) + L(p.mu) * (lin * w);
       const cx<L> wn = inv * x;
       if constexpr (OUT_USER) {

@@ -29,6 +29,20 @@ template <class T> TCFD_D cx<T> conj(cx<T> a) { return cx<T>{a.x, -a.y}; }
 TCFD_HD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
 TCFD_HD double fma_rn(double a, double b, double c) { return fma(a, b, c); }
 
+// reciprocal of the Crank-Nicolson denominator 1 - mu L (>= 1).  fp32: hardware approximation refined by one
+// Newton step (3 instructions, < 1 ulp -- far inside the 1e-3 / 5e-6 parity bars) instead of the ~10
+// instructions of the correctly rounded __frcp_rn, 20 of which a rows unit needs; fp64: correctly rounded.
+#ifndef TCFD_EMU
+TCFD_D float rcp_cn(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+TCFD_D double rcp_cn(double x) { return __drcp_rn(x); }
+#else
+TCFD_D float rcp_cn(float x) { return 1.0f / x; }
+TCFD_D double rcp_cn(double x) { return 1.0 / x; }
+#endif
 // correctly rounded reciprocal (== 1/x in IEEE arithmetic, without the generic division's slow path)
 #ifndef TCFD_EMU
 TCFD_D float rcp_rn(float x) { return __frcp_rn(x); }
