@@ -386,12 +386,17 @@ ns2d_rows3_kernel(const NsParams<T> p) {
       } else {
         w = wst[half * NH + col];
       }
+      // same fused multiply-adds as the dataflow kernel (ns2d_flow.cuh): the two schedules stay bit-identical
       cx<L> h = F;
-      if (p.read_h) h = F + L(p.beta) * hst[half * NH + col];
+      if (p.read_h) {
+        const cx<L> ho = hst[half * NH + col];
+        h = cx<L>{fma_rn(ho.x, p.beta, F.x), fma_rn(ho.y, p.beta, F.y)};
+      }
       if (p.write_h) p.hU_out[ub + half * NH + col] = h;
-      const L den = L(T(1)) - L(p.mu) * lin;
+      const L den = fma_rn(lin, -p.mu, L(T(1)));
       const L inv(rcp_cn(den.lo), rcp_cn(den.hi));
-      const cx<L> x = (w + L(p.gdt) * h) + L(p.mu) * (lin * w);
+      const cx<L> lw{lin * w.x, lin * w.y};
+      const cx<L> x{fma_rn(lw.x, p.mu, fma_rn(h.x, p.gdt, w.x)), fma_rn(lw.y, p.mu, fma_rn(h.y, p.gdt, w.y))};
       const cx<L> wn = inv * x;
       if constexpr (OUT_USER) {
         if (own_a) p.w_out[sb + ra * NH + col] = cx<T>{wn.x.lo, wn.y.lo};
