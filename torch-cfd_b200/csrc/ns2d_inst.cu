@@ -33,6 +33,19 @@ int prep(K kernel, size_t smem, int threads, int* occ) {
   return 0;
 }
 
+// occupancy / shared-memory attributes are PER DEVICE (cudaFuncSetAttribute applies to the current device
+// only): the launchers cache them per device so that one process can drive several GPUs
+constexpr int MAX_DEV = 64;
+inline int cur_dev() {
+#ifndef TCFD_EMU
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEV) d = 0;
+  return d;
+#else
+  return 0;
+#endif
+}
+
 inline int grid_for(int work, int num_sms, int o) {
 #ifdef TCFD_EMU
   (void)num_sms;
@@ -58,7 +71,8 @@ constexpr size_t smem_cols() {
 }
 
 int launch(int which, const NsParams<real_t>& p, int num_sms, cudaStream_t stream) {
-  static int occ[4] = {0, 0, 0, 0};
+  static int occ_all[MAX_DEV][4];
+  int* occ = occ_all[cur_dev()];
   const int nblk_rows = (p.B * (N / 2 + 1) + G - 1) / G;
   const int ntiles = p.B * (N / YT);
   int rc = 0;
@@ -120,7 +134,8 @@ constexpr size_t smem_cols() {
 }
 
 int launch(int which, const NsParams<real_t>& p, const TileMaps* maps, int num_sms, cudaStream_t stream) {
-  static int occ[7] = {0, 0, 0, 0, 0, 0, 0};
+  static int occ_all[MAX_DEV][7];
+  int* occ = occ_all[cur_dev()];
   const int nunits = p.B * (N / 4 + 1);
   const int nquads = p.B * (N / 4);
   int rc = 0;
@@ -186,7 +201,8 @@ constexpr int FLOW_MINB = FLOW_BY_SMEM < 1 ? 1 : (FLOW_BY_SMEM < TCFD_FLOW_MINB 
 template <int GR, int GC, int MAXR, int MODE = 0>
 int launch_flow_g(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms, cudaStream_t stream,
                   const tcfd_flow_window_t* win) {
-  static int occ = 0;
+  static int occ_all[MAX_DEV];
+  int& occ = occ_all[cur_dev()];
   auto k = ns2d_flow_kernel<real_t, N, (MAXR > 0 ? MAXR : FLOW_MINB), GR, GC, MODE>;
   constexpr size_t smem = (MODE & 2) ? FLOW_SMEM2 : FLOW_SMEM;
   int rc = 0;

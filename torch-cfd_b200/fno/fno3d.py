@@ -52,7 +52,7 @@ class FNO3d(nn.Module):
         """Host copies of layer k's pointwise weights (they travel as a kernel parameter), cached until a
         parameter is modified in place (``_version``) or replaced."""
         ps = (mlp.mlp1.weight, mlp.mlp1.bias, mlp.mlp2.weight, mlp.mlp2.bias, w.weight, w.bias)
-        tag = tuple((id(t), t._version) if t is not None else None for t in ps)
+        tag = tuple((id(t), t._version, str(t.device)) if t is not None else None for t in ps)
         cache = self.__dict__.setdefault("_glue_cache", {})
         hit = cache.get(k)
         if hit is None or hit[0] != tag:
@@ -64,7 +64,7 @@ class FNO3d(nn.Module):
         """W = W2 W1 (1 x width), b = W2 b1 + b2 of the activation-free projection MLP, accumulated in
         float64 and cached until a parameter changes."""
         ps = (self.q.mlp1.weight, self.q.mlp1.bias, self.q.mlp2.weight, self.q.mlp2.bias)
-        tag = tuple((id(t), t._version) if t is not None else None for t in ps)
+        tag = tuple((id(t), t._version, str(t.device)) if t is not None else None for t in ps)
         hit = self.__dict__.get("_q_cache")
         if hit is None or hit[0] != tag:
             w1 = ps[0].detach().double().reshape(ps[0].shape[0], -1)
