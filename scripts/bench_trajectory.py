@@ -42,7 +42,8 @@ t0 = time.perf_counter()
 out = T.get_trajectory_imex_sharded(ns, w0, DT, num_steps=a.steps, record_every_steps=a.every, fields=fields, device_result=True)
 torch.cuda.synchronize()
 t_dev = time.perf_counter() - t0
-host = {k: v.cpu() for k, v in out.items()}
+from torch_cfd_b200.solvers import _to_host  # what get_trajectory_imex(..., device_result=False) does
+host = {k: _to_host(v) for k, v in out.items()}
 t_all = time.perf_counter() - t0
 shape = tuple(next(iter(out.values())).shape)
 finite = bool(torch.isfinite(torch.view_as_real(next(iter(out.values()))[:, -1])).all().item())

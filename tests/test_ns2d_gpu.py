@@ -316,3 +316,24 @@ def test_imex_steppers_vs_reference_golden(tag, kw):
                     / torch.linalg.norm(torch.from_numpy(g[f"{tag}_w_{s}"]))).item() < 1e-11
         if tag == "o15":
             assert ns._plans[0].last_launch_count in (1, 1 + 2 * 3)  # one sub-stage per step, fused
+
+
+@pytest.mark.gpu
+def test_staged_device_to_host_copy_equals_cpu():
+    """The pinned-ring device->host copy used for trajectory results: bit-identical to ``.cpu()`` for
+    complex and real tensors whose size is not a multiple of the ring (and small ones take ``.cpu()``)."""
+    from torch_cfd_b200 import solvers
+    torch.manual_seed(3)
+    old = solvers._RING_BYTES
+    solvers._RING_BYTES = 16 << 20  # several chunks with a ragged tail
+    solvers._RING.clear()
+    try:
+        x = torch.randn(7, 9, 256, 129, dtype=torch.complex64, device=DEV)   # 16.6 M complex = 133 MB
+        y = torch.randn(3_000_001, 5, device=DEV, dtype=torch.float64)
+        z = torch.randn(100, device=DEV)
+        for t in (x, y, z, x[:, ::2]):
+            h = solvers._to_host(t)
+            assert not h.is_cuda and h.dtype == t.dtype and torch.equal(h, t.cpu())
+    finally:
+        solvers._RING_BYTES = old
+        solvers._RING.clear()
