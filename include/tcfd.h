@@ -44,7 +44,7 @@ const char* tcfd_version(void);
 typedef struct tcfd_ns2d tcfd_ns2d_t;
 
 typedef struct {
-  int n;         /* grid is n x n, n a power of two in [32, 2048] */
+  int n;         /* grid is n x n, n a power of two in [32, 2048] (fp64: up to 1024) */
   int prec;      /* 32 or 64: precision of every table and of the state */
   int max_batch; /* workspace is sized for this many samples */
   /* HOST pointers, copied at creation.  They are the reference's own buffers

@@ -144,6 +144,11 @@ def test_unsupported_size_is_reported():
     z = torch.zeros(n, n // 2 + 1)
     with pytest.raises(RuntimeError, match="unsupported grid size"):
         _lib.NS2DPlan(lib, n, torch.float32, 1, torch.zeros(n), torch.zeros(n // 2 + 1), z, z, None, None)
+    n = 2048  # fp64 stops at 1024: the column tile would not fit in shared memory
+    z = torch.zeros(n, n // 2 + 1, dtype=torch.float64)
+    with pytest.raises(RuntimeError, match="fp32 only"):
+        _lib.NS2DPlan(lib, n, torch.float64, 1, torch.zeros(n, dtype=torch.float64),
+                      torch.zeros(n // 2 + 1, dtype=torch.float64), z, z, None, None)
 
 
 def test_product_library_exports_every_declared_symbol():

@@ -414,6 +414,9 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
   if (!find_entry(d->prec, d->n, &e))
     return fail(TCFD_ERR_INVALID, "unsupported grid size n=" + std::to_string(d->n) +
                                       " (supported: powers of two 32..2048)");
+  if (d->prec == 64 && d->n > 1024)
+    return fail(TCFD_ERR_INVALID, "n = " + std::to_string(d->n) + " is served in fp32 only (the fp64 column tile of " +
+                                      std::to_string((d->n / 2 + 1) * 256 / 1024) + " KB does not fit in shared memory)");
   tcfd_ns2d* h = new tcfd_ns2d();
   h->n = d->n;
   h->nh = d->n / 2 + 1;
