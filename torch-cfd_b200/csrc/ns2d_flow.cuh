@@ -8,15 +8,18 @@
 //
 //   * items are handed out in a fixed order by a global ticket counter; the order is CHUNK-MAJOR:
 //     for each chunk of W samples -> [prologue rows] -> { [cols], [rows] } x (steps x stages), each
-//     phase sample-major, so a chunk's state, H and advt (W slots each, re-used by the next chunk:
-//     the lines are overwritten in L2 before they are ever evicted dirty) live in the 126 MB L2 from
-//     the first to the last substage of the call;
+//     phase sample-major; the workspaces (state, H, advt) hold W slots that the next chunk re-uses.
+//     (A small W keeps them in the 126 MB L2 -- DRAM traffic drops 7x -- but the step is not DRAM
+//     bound and a short window is limited by the per-sample dependency chain: measured best W = 64,
+//     see profiles/r04_flow_sweep.md);
 //   * the dependencies (a cols item needs every rows unit of its sample and substage, a rows unit
 //     every cols quad of the previous phase) are per-sample counters in global memory: producers
 //     add 1 with release semantics, the consumer's thread 0 polls with acquire semantics.  An item
 //     only ever waits for items with SMALLER tickets, which are already held by resident CTAs, so
 //     the schedule cannot deadlock whatever the number of resident CTAs is (the polling loop is
-//     nevertheless bounded by the SM clock and reports through an error word instead of hanging);
+//     nevertheless bounded by the SM clock: it raises a host-visible error word and traps instead of
+//     hanging).  Every consumer read of another CTA's stores goes through the TMA / bulk-copy engine
+//     (L2, never a possibly stale L1 line), behind acquire + fence.proxy.async;
 //   * the next ticket is fetched while the current item is processed;
 //   * an item is a GROUP of consecutive units of one sample (GR double rows / GC column quads): one
 //     ticket, one dependency poll and one release per group, and inside the group the inputs of unit
@@ -143,25 +146,6 @@ TCFD_D void flow_proxy_fence() {
   asm volatile("fence.proxy.async.global;" ::: "memory");
 #endif
 }
-template <class V>
-TCFD_D V flow_ld_cg(const V* p) {  // L2-only load: the line may have been rewritten by another SM
-#ifndef TCFD_EMU
-  return __ldcg(p);
-#else
-  return *p;
-#endif
-}
-#ifndef TCFD_EMU
-TCFD_D cx<f2> flow_ld_cg(const cx<f2>* p) {
-  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
-  return cx<f2>{f2(v.x, v.y), f2(v.z, v.w)};
-}
-TCFD_D cx<d2> flow_ld_cg(const cx<d2>* p) {
-  const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
-  return cx<d2>{d2(a.x, a.y), d2(b.x, b.y)};
-}
-#endif
-
 // ------------------------------------------------------------------------------------------ smem
 // One layout for both roles:
 //   cols: [ tile ]                                              [ buf ] [ barriers ]
