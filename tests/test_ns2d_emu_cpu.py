@@ -93,6 +93,28 @@ def test_emu_flow_schedule_matches_two_launch_schedule(monkeypatch):
     assert rel_l2(res[("1", "2")][0], ref) < 2e-6
 
 
+def test_emu_flow_grouped_items_512(monkeypatch):
+    """The grouped-item variant of the dataflow kernel (3 double rows / 4 column quads per ticket, units
+    pipelined inside the item, cross-item staging) is what 512^2 and larger grids run by default with a wide
+    window; here it is forced (TCFD_FLOW_G) on a two-sample batch with a one-sample window, so that the
+    slots are re-used, and checked against the oracle."""
+    n, batch, dtype = 512, 2, torch.float32
+    tb = oracle_tables(n, dtype, 1e-3, 0.1, "vorticity", True)
+    w0 = O.synthetic_vorticity_hat(n, batch, 7, dtype)
+    beta, gdt, mu = substage_scalars(dtype, 1e-3)
+    monkeypatch.setenv("TCFD_FLOW", "1")
+    monkeypatch.setenv("TCFD_FLOW_W", "1")
+    monkeypatch.setenv("TCFD_FLOW_G", "3,4,4")
+    plan = emu_plan(tb, batch, dtype)
+    out, dw = torch.empty_like(w0), torch.empty_like(w0)
+    plan.step(w0, out, dw, 1, beta, gdt, mu, 1e3)
+    assert plan.last_launch_count == 1
+    ref, dref = O.forward(tb, w0, 1e-3, 1)
+    assert rel_l2(out, ref) < 2e-6
+    assert (torch.linalg.norm(dw - dref) * 1e-3 / torch.linalg.norm(ref)).item() < 2e-6
+    plan.close()
+
+
 def test_emu_imex_crank_nicolson_is_one_fused_substage():
     """IMEXStepper(order=1.5) (torch_cfd/equations.py:176-193) == one sub-stage of the fused step
     (beta 0, gamma dt = dt, mu = dt/2): kernels against the reference-generated fixture; and the host
