@@ -246,14 +246,11 @@ int launch_flow(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms,
   constexpr int MR_RAW = (sizeof(real_t) == 4 ? 256 : 128) / NT;
   constexpr int MR = MR_RAW < 1 ? 1 : MR_RAW;
   int gr = (win && win->grouped) ? 3 : 1, gc = (win && win->grouped) ? 4 : 1, mr = MR;
-  static int egr = -1, egc = 0, emr = 0;
-  if (egr < 0) {
-    egr = 0;
-    if (const char* e = getenv("TCFD_FLOW_G")) {
-      int a = 0, b = 0, c = 0;
-      const int nf = sscanf(e, "%d,%d,%d", &a, &b, &c);
-      if (nf >= 2) { egr = a; egc = b; emr = nf == 3 ? c : 0; }
-    }
+  int egr = 0, egc = 0, emr = 0;  // read at every call: the variable is an experiment / test knob
+  if (const char* e = getenv("TCFD_FLOW_G")) {
+    int a = 0, b = 0, c = 0;
+    const int nf = sscanf(e, "%d,%d,%d", &a, &b, &c);
+    if (nf >= 2) { egr = a; egc = b; emr = nf == 3 ? c : 0; }
   }
   if (egr > 0) { gr = egr; gc = egc; mr = emr; }
 #define TCFD_FLOW_CASE(A, B, C) if (gr == A && gc == B && mr == C) return launch_flow_g<A, B, C>(fp, maps, num_sms, stream, win);
