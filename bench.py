@@ -30,6 +30,14 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 VISC, DRAG, DT = 1e-3, 0.1, 1e-3
+# ONE unit string for both arms (the driver pairs the arms on metric / unit / direction); what a step
+# is -- batch, grid, per-GPU -- lives in `config`
+UNIT = "steps/s"
+
+
+def workload_name(n, batch, dtype):
+    """The same string in both arms."""
+    return f"Kolmogorov-forced 2D vorticity RK4+CN, {n}x{n}, batch {batch} per GPU, {dtype}"
 
 
 def parse():
@@ -143,13 +151,14 @@ def run_reference(a):
     k = max(1, min(k, int(60.0 * per)))
     v, el = cpu_reference_steps_per_s(a.n, a.batch, dtype, k, threads)
     sample = f"{k} full steps of the {a.batch} x {a.n}^2 batch after 1 warm-up step, torch CPU, {threads} threads"
-    unit = f"steps/s (one step = {a.batch} x {a.n}^2 samples, RK4+CN)"
+    unit = UNIT
     _emit(json.dumps({
         "impl": "reference", "metric": "rk4_spectral_steps_per_sec", "value": v, "unit": unit,
         "n_gpus": a.gpus, "steps": k, "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "f64",
         "data": "synthetic",
-        "config": {"workload": f"Kolmogorov-forced 2D vorticity RK4+CN, {a.n}x{a.n}, batch {a.batch}, {a.dtype}",
+        "config": {"workload": workload_name(a.n, a.batch, a.dtype),
+                   "step": f"one RK4+CN step (5 substages) of {a.batch} x {a.n}^2 samples",
                    "note": "CPU arm: rank 0 only, one batch regardless of --gpus"},
         "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -291,14 +300,17 @@ def run_ours(a):
     except (OSError, KeyError, ValueError):
         pass
     step_us = sum(v["ms_total"] for v in kt.values() if isinstance(v, dict)) * 1e3 / kt["steps"]
-    unit = f"steps/s (one step = {B} x {n}^2 samples per GPU, RK4+CN)"
+    unit = UNIT
     if e2e:
         e2e["unit"] = unit
     out = {
         "metric": "rk4_spectral_steps_per_sec", "value": value, "unit": unit, "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
-        "config": {"workload": f"Kolmogorov-forced 2D vorticity RK4+CN, {n}x{n}, batch {B} per GPU, {a.dtype}",
+        "config": {"workload": workload_name(n, B, a.dtype),
+                   "step": f"one RK4+CN step (5 substages) of {B} x {n}^2 samples on every GPU",
+                   "aggregate": "value and e2e.value are whole-job: steps/s summed over the GPUs (weak scaling, "
+                                "every GPU steps its own batch); the reference arm steps ONE batch on the host cores",
                    "global_batch": B * world, "viscosity": VISC, "drag": DRAG, "dt": DT,
                    "l2": f"working set (state w+h {2 * S * B / 1e6:.0f} MB + workspace) exceeds the 126 MB L2; no flush",
                    "schedule": "dataflow (1 launch per call)" if flow else "two launches per substage",

@@ -70,51 +70,6 @@ _RK4 = {
 }
 
 
-class RK4CrankNicolsonStepper(nn.Module):
-    """Low-storage Runge-Kutta (Carpenter-Kennedy 2N) for the explicit terms with Crank-Nicolson
-    for the implicit ones (reference: torch_cfd/equations.py:249-358).
-
-    ``params`` holds ``alphas`` (len s+1), ``betas`` and ``gammas`` (len s) exactly like upstream.
-    For a libtcfd-backed equation the whole step is fused on the GPU; any other
-    ``ImplicitExplicitODE`` takes the generic sub-stage loop.
-    """
-
-    def __init__(self, order: float = 4, requires_grad: bool = False, weights: Optional[Params] = None,
-                 low_storage: bool = True, *args, **kwargs):
-        super().__init__()
-        self.order = order
-        table = _CK if low_storage else _RK4
-        params = {k: torch.tensor(v) for k, v in table.items()}
-        self.params = nn.ParameterDict({k: nn.Parameter(v, requires_grad=requires_grad) for k, v in params.items()})
-        self.requires_grad = requires_grad
-
-    def substage_scalars(self, dt: float, params: Optional[Params] = None):
-        """(beta_k, gamma_k*dt, mu_k) for every substage, evaluated with the same tensor
-        arithmetic (and therefore the same rounding) as upstream equations.py:355-357."""
-        params = self.params if params is None else params
-        alphas, betas, gammas = params["alphas"], params["betas"], params["gammas"]
-        beta, gdt, mu = [], [], []
-        for k in range(len(betas)):
-            beta.append(float(betas[k]))
-            gdt.append(float(gammas[k] * dt))
-            mu.append(float(0.5 * dt * (alphas[k + 1] - alphas[k])))
-        return beta, gdt, mu
-
-    def forward(self, u: torch.Tensor, dt: float, equation: ImplicitExplicitODE,
-                params: Optional[Params] = None) -> torch.Tensor:
-        if isinstance(equation, NavierStokes2DSpectral):
-            return equation._fused_steps(u, dt, 1, self, params, want_dudt=False)[0]
-        params = self.params if params is None else params
-        alphas, betas, gammas = params["alphas"], params["betas"], params["gammas"]
-        F, G, G_inv = equation.explicit_terms, equation.implicit_terms, equation.implicit_solve
-        h = 0
-        for k in range(len(betas)):
-            h = F(u) + betas[k] * h
-            mu = 0.5 * dt * (alphas[k + 1] - alphas[k])
-            u = G_inv(u + gammas[k] * dt * h + mu * G(u), mu)
-        return u
-
-
 class IMEXStepper(nn.Module):
     """Implicit-explicit steppers of configurable order (reference: torch_cfd/equations.py:110-246):
     order 1 / 1.5 -> ``g = u + dt F(u) + (1 - alpha) dt G(u); u = G_inv(g, alpha dt)`` (:176-193),
@@ -161,6 +116,55 @@ class IMEXStepper(nn.Module):
         u = G_inv(g + dt * h, beta * dt)
         h = alpha * F(u) + (1 - alpha) * h
         return G_inv(g + dt * h, beta * dt)
+
+
+class RK4CrankNicolsonStepper(IMEXStepper):
+    """Low-storage Runge-Kutta (Carpenter-Kennedy 2N) for the explicit terms with Crank-Nicolson
+    for the implicit ones (reference: torch_cfd/equations.py:249-358).
+
+    ``params`` holds ``alphas`` (len s+1), ``betas`` and ``gammas`` (len s) exactly like upstream, and the
+    class derives from ``IMEXStepper`` as upstream does (``isinstance(solver, IMEXStepper)`` keeps its meaning).
+    For a libtcfd-backed equation the whole step is fused on the GPU; any other
+    ``ImplicitExplicitODE`` takes the generic sub-stage loop.
+    """
+
+    def __init__(self, order: float = 4, requires_grad: bool = False, weights: Optional[Params] = None,
+                 low_storage: bool = True, *args, **kwargs):
+        nn.Module.__init__(self)  # upstream calls IMEXStepper.__init__(order) and then replaces params
+        self.order = order
+        table = _CK if low_storage else _RK4
+        params = {k: torch.tensor(v) for k, v in table.items()}
+        self.params = nn.ParameterDict({k: nn.Parameter(v, requires_grad=requires_grad) for k, v in params.items()})
+        self.requires_grad = requires_grad
+
+    def fusable(self, dt: float, params: Optional[Params] = None) -> bool:
+        return True
+
+    def substage_scalars(self, dt: float, params: Optional[Params] = None):
+        """(beta_k, gamma_k*dt, mu_k) for every substage, evaluated with the same tensor
+        arithmetic (and therefore the same rounding) as upstream equations.py:355-357."""
+        params = self.params if params is None else params
+        alphas, betas, gammas = params["alphas"], params["betas"], params["gammas"]
+        beta, gdt, mu = [], [], []
+        for k in range(len(betas)):
+            beta.append(float(betas[k]))
+            gdt.append(float(gammas[k] * dt))
+            mu.append(float(0.5 * dt * (alphas[k + 1] - alphas[k])))
+        return beta, gdt, mu
+
+    def forward(self, u: torch.Tensor, dt: float, equation: ImplicitExplicitODE,
+                params: Optional[Params] = None) -> torch.Tensor:
+        if isinstance(equation, NavierStokes2DSpectral):
+            return equation._fused_steps(u, dt, 1, self, params, want_dudt=False)[0]
+        params = self.params if params is None else params
+        alphas, betas, gammas = params["alphas"], params["betas"], params["gammas"]
+        F, G, G_inv = equation.explicit_terms, equation.implicit_terms, equation.implicit_solve
+        h = 0
+        for k in range(len(betas)):
+            h = F(u) + betas[k] * h
+            mu = 0.5 * dt * (alphas[k + 1] - alphas[k])
+            u = G_inv(u + gammas[k] * dt * h + mu * G(u), mu)
+        return u
 
 
 def _probe_state_independent(forcing_fn, grid: Grid, vorticity: bool) -> bool:
@@ -317,9 +321,12 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
     def forward(self, vort_hat, dt, steps=1) -> Tuple[torch.Tensor, torch.Tensor]:
         """vort_hat: (B, n, n//2+1), (n_t, n, n//2+1) or (n, n//2+1) complex spectrum.
         Returns (vort_hat after ``steps`` steps, (new - old) / (steps * dt))."""
-        if isinstance(self.solver, RK4CrankNicolsonStepper):
-            return self._fused_steps(vort_hat, dt, steps, self.solver)
-        if isinstance(self.solver, IMEXStepper) and self.solver.fusable(dt):
+        if torch.is_grad_enabled() and (vort_hat.requires_grad or (
+                self.solver is not None and any(p.requires_grad for p in self.solver.parameters()))):
+            raise NotImplementedError(
+                "torch-cfd_b200: the CUDA step is inference-only (no autograd through the solver, SURVEY 8b); "
+                "run it under torch.no_grad() or detach the state / freeze the stepper parameters")
+        if isinstance(self.solver, IMEXStepper) and self.solver.fusable(dt):  # includes RK4CrankNicolsonStepper
             return self._fused_steps(vort_hat, dt, steps, self.solver)
         if self.solver is None:
             raise TypeError("NavierStokes2DSpectral.solver is None: pass solver=RK4CrankNicolsonStepper()")

@@ -16,7 +16,8 @@ from typing import Dict, Optional, Sequence
 
 import torch
 
-from .equations import NavierStokes2DSpectral, RK4CrankNicolsonStepper
+from .equations import IMEXStepper, NavierStokes2DSpectral
+from .spectral import vorticity_to_velocity
 
 FIELDS = ("vorticity", "stream", "vort_t", "residual")
 
@@ -66,8 +67,10 @@ def _trajectory_device(equation, w0, dt, num_steps, record_every_steps, dtype, f
     """Snapshots on the device of ``w0``: dict field -> (B, n_t, n, nh) tensor of ``dtype``."""
     rec = _record_steps(num_steps, record_every_steps)
     n_t = len(rec)
-    fused = isinstance(equation, NavierStokes2DSpectral) and isinstance(equation.solver, RK4CrankNicolsonStepper) \
-        and w0.is_cuda
+    # every stepper the fused launch serves: RK4CrankNicolsonStepper (an IMEXStepper, as upstream) and the
+    # order-1 / 1.5 IMEXStepper with alpha = 0.5; other IMEX settings take the generic loop below
+    fused = isinstance(equation, NavierStokes2DSpectral) and isinstance(equation.solver, IMEXStepper) \
+        and equation.solver.fusable(dt) and w0.is_cuda
     n, nh = w0.shape[-2:]
     w = w0.detach().reshape(-1, n, nh).contiguous()
     B = w.shape[0]
@@ -96,7 +99,10 @@ def _trajectory_device(equation, w0, dt, num_steps, record_every_steps, dtype, f
             w, dwdt = equation.forward(w, dt=dt)
             vals = {"vorticity": w, "vort_t": dwdt}
             if snaps["stream"] is not None:
-                vals["stream"] = equation.stream_function(w)
+                if hasattr(equation, "stream_function"):
+                    vals["stream"] = equation.stream_function(w)
+                else:  # what upstream does for any equation (fno/data_gen/solvers.py:230-231)
+                    vals["stream"] = vorticity_to_velocity(equation.grid, w, (equation.kx, equation.ky))[1]
             if snaps["residual"] is not None:
                 vals["residual"] = equation.residual(w, dwdt)
             for k, v in vals.items():
