@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Schedule sweep of hot path A on one GPU: two-launch schedule vs the persistent dataflow schedule at
-several window sizes W and H sub-windows Wh (configs "flow:W[:Wh]"; TCFD_FLOW / TCFD_FLOW_W /
-TCFD_FLOW_WH are read when a plan is created).  Prints one line
-per configuration and checks that every schedule returns bit-identical states."""
+several window sizes W and kernel variants (configs "flow:W[:G]" with G = "GR.GC.MINB" -> TCFD_FLOW_G, only
+honoured by -DTCFD_FLOW_VARIANTS builds; TCFD_FLOW / TCFD_FLOW_W are read when a plan is created).  Prints
+one line per configuration and checks that every schedule returns bit-identical states."""
 import argparse
 import json
 import os
@@ -30,12 +30,15 @@ def main():
     w0 = make_state(n, B, torch.float32, 0).to(dev)
     ref = None
     for cfg in a.configs.split(","):
-        f = cfg.split(":")  # flow : W [: Wh]
+        f = cfg.split(":")  # flow : W [: G]
         flow, W = f[0], f[1]
-        Wh = f[2] if len(f) > 2 else "8"
+        G = f[2].replace(".", ",") if len(f) > 2 else ""
         os.environ["TCFD_FLOW"] = flow
         os.environ["TCFD_FLOW_W"] = W if int(W) > 0 else "64"
-        os.environ["TCFD_FLOW_WH"] = Wh
+        if G:
+            os.environ["TCFD_FLOW_G"] = G
+        else:
+            os.environ.pop("TCFD_FLOW_G", None)
         grid = T.Grid(shape=(n, n), domain=((0, diam), (0, diam)))
         forcing = T.KolmogorovForcing(diam=diam, wave_number=1, grid=grid, scale=1, vorticity=True)
         ns = T.NavierStokes2DSpectral(viscosity=VISC, grid=grid, drag=DRAG, smooth=True, forcing_fn=forcing,
@@ -51,7 +54,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        rec = {"flow": int(flow), "W": int(W), "Wh": int(Wh), "n": n, "batch": B, "steps_per_s": a.steps / (ms * 1e-3),
+        rec = {"flow": int(flow), "W": int(W), "G": G, "n": n, "batch": B, "steps_per_s": a.steps / (ms * 1e-3),
                "launches_per_step": ns._plans[0].last_launch_count}
         if a.multi:
             w2, _ = ns(w0, DT, steps=a.multi)  # warm

@@ -189,6 +189,66 @@ def test_fp32_drift_1000_steps_256():
         assert e < 1e-3, e
 
 
+def test_horizon_c3_2000_steps_512_fp32():
+    """BASELINE configs[2] horizon: 512^2, fp32, Kolmogorov forced, drag 0.1, 2000 steps,
+    2 samples against the fp32 oracle -- the north-star bar (rel-L2 of the physical field <= 1e-3) -- and
+    against the fp64 oracle, to separate implementation error from the fp32 drift both fp32 runs share."""
+    n, steps = 512, 2000
+    w0 = O.synthetic_vorticity_hat(n, 2, 77, torch.float32)
+    with default_dtype(torch.float32):
+        ns = build_module(n, torch.float32, 1e-3, 0.1, "vorticity")
+        w, _ = ns(w0.to(DEV), 1e-3, steps=steps)
+        tb = oracle_tables(n, torch.float32, 1e-3, 0.1, "vorticity")
+        wr, _ = O.forward(tb, w0, 1e-3, steps)
+    with default_dtype(torch.float64):
+        tb64 = oracle_tables(n, torch.float64, 1e-3, 0.1, "vorticity")
+        w64, _ = O.forward(tb64, w0.to(torch.complex128), 1e-3, steps)
+    f = torch.fft.irfft2(w.cpu().to(torch.complex128))
+    f32 = torch.fft.irfft2(wr.to(torch.complex128))
+    f64 = torch.fft.irfft2(w64)
+    e_ours_vs_ref32, e_ours_vs_64, e_ref32_vs_64 = rel_l2(f, f32), rel_l2(f, f64), rel_l2(f32, f64)
+    print(f"2000 steps 512^2 fp32: ours vs fp32 oracle {e_ours_vs_ref32:.3e}, ours vs fp64 oracle {e_ours_vs_64:.3e}, "
+          f"fp32 oracle vs fp64 oracle {e_ref32_vs_64:.3e}")
+    assert e_ours_vs_ref32 < 1e-3, e_ours_vs_ref32   # the bar
+    assert e_ours_vs_64 < 1e-3, e_ours_vs_64
+    # our fp32 error against the exact (fp64) trajectory is of the size of the reference's own
+    assert e_ours_vs_64 < 3 * e_ref32_vs_64 + 1e-5, (e_ours_vs_64, e_ref32_vs_64)
+
+
+def test_horizon_c2_1000_steps_256x64_fp32():
+    """BASELINE configs[1] as stated: 256^2 x 64, fp32, unforced, 1000 steps; oracle check of 3 samples and
+    batch independence of the same 3 samples stepped alone."""
+    n, batch, steps, dtype = 256, 64, 1000, torch.float32
+    with default_dtype(dtype):
+        ns = build_module(n, dtype, 1e-3, 0.0, None)
+        tb = oracle_tables(n, dtype, 1e-3, 0.0, None)
+        base = O.synthetic_vorticity_hat(n, 4, 5, dtype)
+        w0 = torch.stack([base[i % 4] * (1.0 + 0.01 * i) for i in range(batch)])
+        idx = [0, 29, batch - 1]
+        w, _ = ns(w0.to(DEV), 1e-3, steps=steps)
+        wr, _ = O.forward(tb, w0[idx], 1e-3, steps)
+        e = rel_l2(torch.fft.irfft2(w[idx].cpu()), torch.fft.irfft2(wr))
+        print(f"1000 steps 256^2 x 64 fp32: rel-L2 vs fp32 oracle {e:.3e}")
+        assert e < 1e-3, e
+        sub, _ = ns(w0[idx].to(DEV), 1e-3, steps=steps)
+        assert torch.equal(sub, w[idx])
+
+
+def test_horizon_512_fp64_100_steps():
+    """fp64 bar at the target grid: 512^2, forced, 100 steps, 2 samples, rel-L2 <= 1e-6 (achieved ~1e-12)."""
+    n, dtype = 512, torch.float64
+    with default_dtype(dtype):
+        ns = build_module(n, dtype, 1e-3, 0.1, "vorticity")
+        tb = oracle_tables(n, dtype, 1e-3, 0.1, "vorticity")
+        w0 = O.synthetic_vorticity_hat(n, 2, 78, dtype)
+        w, _ = ns(w0.to(DEV), 1e-3, steps=100)
+        wr, _ = O.forward(tb, w0, 1e-3, 100)
+        e = rel_l2(torch.fft.irfft2(w.cpu()), torch.fft.irfft2(wr))
+        print(f"100 steps 512^2 fp64: rel-L2 vs oracle {e:.3e}")
+        assert e < 1e-6, e
+        assert e < 1e-10, e
+
+
 def test_get_trajectory_imex_vs_reference_golden():
     """recorded (w, psi, dw/dt, residual), complex64, (B, n_t, n, nh), CPU result."""
     import torch_cfd_b200 as T

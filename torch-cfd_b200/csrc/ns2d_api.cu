@@ -186,7 +186,6 @@ void fill_params(const tcfd_ns2d* h, tcfd::NsParams<T>& p, int batch) {
   p.H2 = static_cast<T*>(h->H);
   p.advt2 = static_cast<T*>(h->advt);
   p.NDF = (h->KF + 1) / 2;
-  p.Hplane = (size_t)h->chunk * h->nh * h->n;
   p.tab = static_cast<const tcfd::tab4<T>*>(h->tab);
   p.frow = static_cast<const unsigned char*>(h->frow);
   p.tabU = h->tabU;
@@ -201,16 +200,15 @@ void fill_params(const tcfd_ns2d* h, tcfd::NsParams<T>& p, int batch) {
   p.fhat = static_cast<const tcfd::cx<T>*>(h->fhat);
 }
 
-// TMA descriptors over H2 = [2 planes][chunk][NH][N] packed-complex entries (4 reals each): a tile
-// is 4 consecutive entries of every row of one sample, in both planes.
+// TMA descriptor over H2 = [chunk][N rows kx][N] packed-complex entries (4 reals each): a tile is 4
+// consecutive entries of every row of one sample.
 int make_tile_maps(tcfd_ns2d* h) {
   const size_t ent = 4 * h->es;
   const size_t row_bytes = (size_t)h->n * ent;
 #ifdef TCFD_EMU
   h->maps.base = static_cast<const unsigned char*>(h->H);
   h->maps.row_bytes = row_bytes;
-  h->maps.sample_bytes = row_bytes * h->nh;
-  h->maps.plane_bytes = row_bytes * h->nh * h->chunk;
+  h->maps.sample_bytes = row_bytes * h->n;
   return 0;
 #else
   void* fn = nullptr;
@@ -220,17 +218,13 @@ int make_tile_maps(tcfd_ns2d* h) {
   auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   const CUtensorMapDataType dt = h->prec == 32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
   const CUtensorMapSwizzle sw = h->prec == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-  const cuuint64_t gdim[4] = {(cuuint64_t)h->n * 4, (cuuint64_t)h->nh, (cuuint64_t)h->chunk, 2};
-  const cuuint64_t gstr[3] = {(cuuint64_t)row_bytes, (cuuint64_t)row_bytes * h->nh, (cuuint64_t)row_bytes * h->nh * h->chunk};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const cuuint32_t rows = (cuuint32_t)((h->nh - 1) < 256 ? (h->nh - 1) : 256);
-  const cuuint32_t box_main[4] = {16, rows, 1, 2};  // 16 reals = 4 entries = 64 B (fp32) / 128 B (fp64)
-  const cuuint32_t box_last[4] = {16, 1, 1, 2};
-  CUresult r = encode(&h->maps.main, dt, 4, h->H, gdim, gstr, box_main, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+  const cuuint64_t gdim[3] = {(cuuint64_t)h->n * 4, (cuuint64_t)h->n, (cuuint64_t)h->chunk};
+  const cuuint64_t gstr[2] = {(cuuint64_t)row_bytes, (cuuint64_t)row_bytes * h->n};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const cuuint32_t rows = (cuuint32_t)(h->n < 256 ? h->n : 256);
+  const cuuint32_t box_main[3] = {16, rows, 1};  // 16 reals = 4 entries = 64 B (fp32) / 128 B (fp64)
+  CUresult r = encode(&h->maps.main, dt, 3, h->H, gdim, gstr, box_main, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r == CUDA_SUCCESS)
-    r = encode(&h->maps.last, dt, 4, h->H, gdim, gstr, box_last, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TCFD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return 0;
 #endif
@@ -477,8 +471,10 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
     const size_t ab = (size_t)h->chunk * (h->n / 4 + 1) * h->n * 4 * h->es;
     // unit-layout state (v2): [B][n/4+1][2][nh] entries of 4 reals
     const size_t ub = (size_t)h->chunk * (h->n / 4 + 1) * 2 * h->nh * 4 * h->es;
-    // H: [B][nh][n/yt][4][yt] = 4 * nh * n complex per sample
-    const size_t hb = (size_t)h->chunk * h->nh * h->n * 4 * 2 * h->es;
+    // H: first generation [B][nh][n/yt][4][yt] = 4 * nh * n complex per sample; second generation
+    // [B][n][n] packed-complex entries of 4 reals (z layout, ns2d_v2.cuh)
+    const size_t hb = h->entry.v2 ? (size_t)h->chunk * h->n * h->n * 4 * h->es
+                                  : (size_t)h->chunk * h->nh * h->n * 4 * 2 * h->es;
     void** bufs[] = {&h->H, &h->advt, &h->wS, &h->hA, &h->wT, &h->hB};  // hot buffers first
     size_t nbs[6];
     for (int i = 0; i < 6; ++i) {

@@ -156,7 +156,7 @@ struct FlowSmem {
   typedef RowsSmem<T, N> R;
   static constexpr int NH = N / 2 + 1;
   static constexpr int IB = 4 * (int)sizeof(cx<L>);
-  typedef TileGeom<NH, IB> G;
+  typedef TileGeom<N, IB> G;
   static constexpr int TABM = R::TAB_BYTES + 2 * R::MASK_ROW;  // one table block + its mask rows
   static constexpr int OFF_W = 0;
   static constexpr int OFF_H = R::UNIT_BYTES;
@@ -169,14 +169,6 @@ struct FlowSmem {
   static constexpr int BYTES = OFF_BAR + 64 + 1024;  // + slack for the 1 KB alignment of the area
 };
 
-// Two of the four spectra at one entry (lanes (psi-derived, w-derived)); a = half ? -kx : ky,
-// b = half ? ky : kx  (bitwise the same values as ns_fields_s<HALF>)
-template <class T>
-TCFD_D cx<typename pack2<T>::type> ns_fields_rt(cx<T> w, T nil, T a, T b) {
-  typedef typename pack2<T>::type L;
-  const T px = nil * w.x, py = nil * w.y;  // psi
-  return cx<L>{L(-(a * py), -(b * w.y)), L(a * px, b * w.x)};
-}
 template <class L>
 TCFD_D cx<typename lane_traits<L>::scalar> lane_rt(cx<L> v, int lane) {
   typedef typename lane_traits<L>::scalar T;
@@ -206,7 +198,7 @@ TCFD_D cx<typename lane_traits<L>::scalar> lane_rt(cx<L> v, int lane) {
     const int pr_ = prof_cur;                                             \
     FLOW_MARK(3);                                                         \
     if constexpr ((MODE & 1) != 0) __syncthreads();                       \
-    else fft_run<L, N, DIR, 1, false, N>(ARR, tw, buf, parity, t, sync);  \
+    else fft_run<L, N, DIR, 1, PP, N>(ARR, tw, buf, parity, t, sync);     \
     FLOW_MARK(pr_);                                                       \
   } while (0)
 #define FLOW_LOADWAIT(BAR, PH)  \
@@ -223,13 +215,6 @@ TCFD_D cx<typename lane_traits<L>::scalar> lane_rt(cx<L> v, int lane) {
     flow_wait(PTR, TGT, fp.err);      \
     FLOW_MARK(pr_);                   \
   } while (0)
-// MODE bit 1: the inverse transforms run two per thread (V = 2: twice the independent work per warp and
-// half the barriers; needs the register budget of 256 resident threads per SM and a 2 N exchange buffer)
-#define FLOW_FFT2(DIR, ARR)                                                   \
-  do {                                                                        \
-    if constexpr ((MODE & 1) != 0) __syncthreads();                           \
-    else fft_run<L, N, DIR, 2, false, 2 * N>(ARR, tw, buf, parity, t, sync);  \
-  } while (0)
 // GR: double rows per rows item, GC: column quads per cols item (GC divides N/4).
 template <class T, int N, int MINB, int GR, int GC, int MODE = 0>
 __global__ void __launch_bounds__(N / 8, MINB)
@@ -239,8 +224,9 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
 #endif
                  TileMaps maps) {
   typedef typename pack2<T>::type L;
-  constexpr bool V2 = (MODE & 2) != 0;
-  typedef FlowSmem<T, N, V2 ? 2 : 1> S;
+  // MODE bit 1: ping-pong exchange buffers (one barrier per exchange instead of two; +N entries of shared memory)
+  constexpr bool PP = (MODE & 2) != 0;
+  typedef FlowSmem<T, N, PP ? 2 : 1> S;
   typedef typename S::G G;
   typedef typename S::R R;
   constexpr int NT = N / 8, NH = N / 2 + 1, ND = N / 4 + 1, NQ = N / 4;
@@ -296,7 +282,6 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
     stage_barrier_init(bar_o);
 #ifndef TCFD_EMU
     tma_prefetch_desc(&maps.main);
-    tma_prefetch_desc(&maps.last);
 #endif
     next_tk = flow_fetch_add(ticket, 1);
     sh[0] = next_tk;
@@ -379,7 +364,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         const int sl2 = u2 / IC, s2 = c2 * W + sl2;
         if (flow_ld_acquire(&cnt_rows[s2]) < IR * (j2 + 1)) return;
         flow_proxy_fence();
-        tile_load_issue<NH, IB>(tile, maps, (u2 % IC) * GC * 4, sl2, bar_s);
+        tile_load_issue<N, IB>(tile, maps, (u2 % IC) * GC * 4, sl2, bar_s);
       } else {
         const int sl2 = u2 / IR, s2 = c2 * W + sl2;
         const bool pro2 = j2 < 0;
@@ -401,7 +386,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
       const int s = c * W + sl;
       if (ctl && !staged) {
         FLOW_DEPWAIT(&cnt_rows[s], IR * (j + 1));
-        tile_load_issue<NH, IB>(tile, maps, q0 * 4, sl, bar_s);
+        tile_load_issue<N, IB>(tile, maps, q0 * 4, sl, bar_s);
       }
 #pragma unroll 1
       for (int g = 0; g < GC; ++g) {
@@ -409,112 +394,40 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         cx<L> cc[1][8];
         FLOW_LOADWAIT(bar_s, phase_s);
         phase_s ^= 1u;
-        if constexpr (V2) {
 #pragma unroll
-          for (int pr = 0; pr < 2; ++pr) {
-            cx<L> z[2][8];
+        for (int cidx = 0; cidx < 4; ++cidx) {
+          cx<L> z[1][8];
 #pragma unroll
-            for (int v = 0; v < 2; ++v)
-#pragma unroll
-              for (int m = 0; m < 8; ++m) {
-                const int k = t + m * NT;
-                const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
-                const int row = lo ? k : N - k;
-                const cx<L> A = tile_ld<T, G>(tile, row, 0, 2 * pr + v);
-                const cx<L> Bv = tile_ld<T, G>(tile, row, 1, 2 * pr + v);
-                z[v][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
-                if ((m == 0 || m == 4) && t == 0) z[v][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
-              }
-            FLOW_FFT2(+1, z);
-            if (pr == 1) {
-              // every thread has passed a barrier after its last tile read: the tile is free
-              if (ctl) {
-                if (g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
-                else try_stage_next(false);
-              }
-            }
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const T adv0 = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
-              const T adv1 = -(z[1][m].x.hi * z[1][m].x.lo + z[1][m].y.hi * z[1][m].y.lo);
-              if (pr == 0) { cc[0][m].x.lo = adv0; cc[0][m].y.lo = adv1; }
-              else { cc[0][m].x.hi = adv0; cc[0][m].y.hi = adv1; }
+          for (int m = 0; m < 8; ++m) z[0][m] = tile_ld<T, G>(tile, t + m * NT, cidx);
+          FLOW_FFT(+1, z);
+          if (cidx == 3) {
+            // every thread has passed a barrier after its last tile read: the tile is free
+            if (ctl) {
+              if (g + 1 < GC) tile_load_issue<N, IB>(tile, maps, y0 + 4, sl, bar_s);
+              else try_stage_next(false);
             }
           }
-        } else if constexpr ((MODE & 32) != 0) {
-          // the four columns share ONE copy of the unpack + transform code (smaller instruction footprint)
-#pragma unroll 1
-          for (int cidx = 0; cidx < 4; ++cidx) {
-            cx<L> z[1][8];
-  #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const int k = t + m * NT;
-              const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
-              const int row = lo ? k : N - k;
-              const cx<L> A = tile_ld<T, G>(tile, row, 0, cidx);
-              const cx<L> Bv = tile_ld<T, G>(tile, row, 1, cidx);
-              z[0][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
-              if ((m == 0 || m == 4) && t == 0) z[0][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
-              if constexpr ((MODE & 8) != 0) z[0][m] = (m & 1) ? A : Bv;  // timing experiment: no unpack math
-            }
-            FLOW_FFT(+1, z);
-            if (cidx == 3) {
-              // every thread has passed a barrier after its last tile read: the tile is free
-              if (ctl) {
-                if (g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
-                else try_stage_next(false);
-              }
-            }
-  #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const T adv = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
-              if (cidx == 0) cc[0][m].x.lo = adv;
-              if (cidx == 1) cc[0][m].y.lo = adv;
-              if (cidx == 2) cc[0][m].x.hi = adv;
-              if (cidx == 3) cc[0][m].y.hi = adv;
-            }
-          }
-        } else {
 #pragma unroll
-          for (int cidx = 0; cidx < 4; ++cidx) {
-            cx<L> z[1][8];
-  #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const int k = t + m * NT;
-              const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
-              const int row = lo ? k : N - k;
-              const cx<L> A = tile_ld<T, G>(tile, row, 0, cidx);
-              const cx<L> Bv = tile_ld<T, G>(tile, row, 1, cidx);
-              z[0][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
-              if ((m == 0 || m == 4) && t == 0) z[0][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
-              if constexpr ((MODE & 8) != 0) z[0][m] = (m & 1) ? A : Bv;  // timing experiment: no unpack math
-            }
-            FLOW_FFT(+1, z);
-            if (cidx == 3) {
-              // every thread has passed a barrier after its last tile read: the tile is free
-              if (ctl) {
-                if (g + 1 < GC) tile_load_issue<NH, IB>(tile, maps, y0 + 4, sl, bar_s);
-                else try_stage_next(false);
-              }
-            }
-  #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const T adv = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
-              if (cidx == 0) cc[0][m].x.lo = adv;
-              if (cidx == 1) cc[0][m].y.lo = adv;
-              if (cidx == 2) cc[0][m].x.hi = adv;
-              if (cidx == 3) cc[0][m].y.hi = adv;
-            }
+          for (int m = 0; m < 8; ++m) {
+            const T adv = -(z[0][m].x.hi * z[0][m].x.lo + z[0][m].y.hi * z[0][m].y.lo);
+            if (cidx == 0) cc[0][m].x.lo = adv;
+            if (cidx == 1) cc[0][m].y.lo = adv;
+            if (cidx == 2) cc[0][m].x.hi = adv;
+            if (cidx == 3) cc[0][m].y.hi = adv;
           }
         }
         FLOW_FFT(-1, cc);
+        // separation buffer: with ping-pong exchanges it is the half the next exchange would write (the other
+        // half may still be read by slower threads of the transform's last exchange)
+        cx<L>* sbuf = buf + (PP ? parity * N : 0);
+        if (PP) parity ^= 1;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) buf[t + m * NT] = cc[0][m];
+        for (int m = 0; m < 8; ++m) sbuf[t + m * NT] = cc[0][m];
         __syncthreads();
         cx<L>* dst = reinterpret_cast<cx<L>*>(p.advt2) + (size_t)sl * ND * N + y0;
         for (int jj = t; jj < p.NDF; jj += NT) {
           const int k = 2 * jj;
-          const cx<L> c0 = buf[k], c1 = buf[k + 1], n0 = buf[(N - k) % N], n1 = buf[N - k - 1];
+          const cx<L> c0 = sbuf[k], c1 = sbuf[k + 1], n0 = sbuf[(N - k) % N], n1 = sbuf[N - k - 1];
           const L hf(T(0.5));
           const L Ea = hf * (c0.x + n0.x), Fa = hf * (c0.y - n0.y), Ga = hf * (c0.y + n0.y), Ha = hf * (n0.x - c0.x);
           const L Eb = hf * (c1.x + n1.x), Fb = hf * (c1.y - n1.y), Gb = hf * (c1.y + n1.y), Hb = hf * (n1.x - c1.x);
@@ -524,7 +437,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
           o[2] = cx<L>{L(Ea.hi, Eb.hi), L(Fa.hi, Fb.hi)};
           o[3] = cx<L>{L(Ga.hi, Gb.hi), L(Ha.hi, Hb.hi)};
         }
-        if (g + 1 < GC) __syncthreads();  // buf is re-used by the next quad's transforms
+        if (g + 1 < GC && !PP) __syncthreads();  // buf is re-used by the next quad's transforms
       }
       if (ctl) {
         sh[it & 1] = next_tk;
@@ -710,79 +623,48 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
       if (do_inv) {
         FLOW_MARK(6);
         const T ky0 = p.kappa_y[0], kyh = p.kappa_y[N / 2];
-        if constexpr (V2) {
-          // both halves of a lane side by side: (u, dw/dx) -> plane 0, (v, dw/dy) -> plane 1
-#pragma unroll 1
-          for (int lane = 0; lane < (valid1 ? 2 : 1); ++lane) {
-            const T kx1 = lane ? kx1b : kx1a, kx2 = lane ? kx2b : kx2a;
-            const int r1 = lane ? r1b : r1a;
-            const T* nl = nilst + lane * NH;
-            cx<L> z[2][8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const bool lo = m < 4;
-              const T kx = lo ? kx1 : kx2;
-              const T nil = nl[lo ? t + m * NT : N - t - m * NT];
-              const cx<T> wl = lane_rt(wv[m], lane);
-              const cx<L> f0 = ns_fields_rt<T>(wl, nil, kyv[m], kx), f1 = ns_fields_rt<T>(wl, nil, -kx, kyv[m]);
-              z[0][m] = lo ? f0 : conj(f0);
-              z[1][m] = lo ? f1 : conj(f1);
-            }
-            if (t == 0) {
-              const T n0 = nl[0], nh = nl[N / 2];
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const cx<L> f1 = ns_fields_rt<T>(lane_rt(wv[0], lane), n0, half ? -kx1 : ky0, half ? ky0 : kx1);
-                const cx<L> f2_ = ns_fields_rt<T>(lane_rt(e0, lane), n0, half ? -kx2 : ky0, half ? ky0 : kx2);
-                const cx<L> g1 = ns_fields_rt<T>(lane_rt(e1, lane), nh, half ? -kx1 : kyh, half ? kyh : kx1);
-                const cx<L> g2 = ns_fields_rt<T>(lane_rt(wv[4], lane), nh, half ? -kx2 : kyh, half ? kyh : kx2);
-                z[half][0] = L(T(0.5)) * (f1 + conj(f2_));
-                z[half][4] = L(T(0.5)) * (g1 + conj(g2));
-              }
-            }
-            FLOW_FFT2(+1, z);
-            cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + ((size_t)sl * NH + r1) * (size_t)N + t;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) Hrow[m * NT] = z[0][m];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) Hrow[p.Hplane + m * NT] = z[1][m];
-          }
-        } else {
-          const int nq = valid1 ? 4 : 2;
+        // per lane (row pair) two transforms: type 0 ("P" = A + i B) gives row r1 of z, type 1 ("Q" = A - i B,
+        // stored conjugated) row r2 = N - r1 (ns2d_v2.cuh: ns_fields_z); self-paired rows need P only
+        const int nq = valid1 ? 4 : 2;
 #pragma unroll 1
         for (int q = 0; q < nq; ++q) {
-          const int lane = q >> 1, half = q & 1;
+          const int lane = q >> 1, type = q & 1;
+          if (type && (lane ? selfb : selfa)) continue;  // CTA-uniform
           const T kx1 = lane ? kx1b : kx1a, kx2 = lane ? kx2b : kx2a;
-          const int r1 = lane ? r1b : r1a;
+          const int row = lane ? (type ? r2b : r1b) : (type ? r2a : r1a);
           const T* nl = nilst + lane * NH;
+          const T sg = type ? T(-1) : T(1);
           cx<L> z[1][8];
 #pragma unroll
           for (int m = 0; m < 8; ++m) {
             const bool lo = m < 4;
-            const T kx = lo ? kx1 : kx2;
             const T nil = nl[lo ? t + m * NT : N - t - m * NT];
             if constexpr ((MODE & 4) != 0) {  // timing experiment: no field construction
               z[0][m] = wv[m];
               continue;
             }
-            const cx<L> f = ns_fields_rt<T>(lane_rt(wv[m], lane), nil, half ? -kx : kyv[m], half ? kyv[m] : kx);
+            const cx<L> f = ns_fields_z<T>(lane_rt(wv[m], lane), nil, lo ? kx1 : kx2, kyv[m], lo ? sg : -sg);
             z[0][m] = lo ? f : conj(f);
           }
           if (t == 0 && (MODE & 4) == 0) {
             // self-conjugate columns ky = 0 and ky = N/2: Hermitian part of the two rows (C2R semantics)
             const T n0 = nl[0], nh = nl[N / 2];
-            const cx<L> f1 = ns_fields_rt<T>(lane_rt(wv[0], lane), n0, half ? -kx1 : ky0, half ? ky0 : kx1);
-            const cx<L> f2_ = ns_fields_rt<T>(lane_rt(e0, lane), n0, half ? -kx2 : ky0, half ? ky0 : kx2);
-            const cx<L> g1 = ns_fields_rt<T>(lane_rt(e1, lane), nh, half ? -kx1 : kyh, half ? kyh : kx1);
-            const cx<L> g2 = ns_fields_rt<T>(lane_rt(wv[4], lane), nh, half ? -kx2 : kyh, half ? kyh : kx2);
+            const cx<L> f1 = ns_fields_z<T>(lane_rt(wv[0], lane), n0, kx1, ky0, sg);
+            const cx<L> f2_ = ns_fields_z<T>(lane_rt(e0, lane), n0, kx2, ky0, -sg);
+            const cx<L> g1 = ns_fields_z<T>(lane_rt(e1, lane), nh, kx1, kyh, sg);
+            const cx<L> g2 = ns_fields_z<T>(lane_rt(wv[4], lane), nh, kx2, kyh, -sg);
             z[0][0] = L(T(0.5)) * (f1 + conj(f2_));
             z[0][4] = L(T(0.5)) * (g1 + conj(g2));
           }
           FLOW_FFT(+1, z);
-          cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + (size_t)half * p.Hplane + ((size_t)sl * NH + r1) * (size_t)N + t;
+          cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + ((size_t)sl * N + row) * (size_t)N + t;
+          if (type) {
 #pragma unroll
-          for (int m = 0; m < 8; ++m) Hrow[m * NT] = z[0][m];
-        }
+            for (int m = 0; m < 8; ++m) Hrow[m * NT] = conj(z[0][m]);
+          } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) Hrow[m * NT] = z[0][m];
+          }
         }
       }
     }

@@ -130,7 +130,7 @@ constexpr int MINB_COLS = 5;
 constexpr size_t smem_rows() { return (size_t)N * sizeof(cx<lane_t>); }
 constexpr size_t smem_rows3() { return (size_t)RowsSmem<real_t, N>::BYTES; }
 constexpr size_t smem_cols() {
-  return 1024 + (size_t)TileGeom<N / 2 + 1, 4 * (int)sizeof(cx<lane_t>)>::BYTES + (size_t)N * sizeof(cx<lane_t>) + 16;
+  return 1024 + (size_t)TileGeom<N, 4 * (int)sizeof(cx<lane_t>)>::BYTES + (size_t)N * sizeof(cx<lane_t>) + 16;
 }
 
 int launch(int which, const NsParams<real_t>& p, const TileMaps* maps, int num_sms, cudaStream_t stream) {
@@ -193,7 +193,6 @@ int launch(int which, const NsParams<real_t>& p, const TileMaps* maps, int num_s
 #define TCFD_FLOW_MINB MINB_BY_THREADS
 #endif
 constexpr size_t FLOW_SMEM = (size_t)FlowSmem<real_t, N>::BYTES;       // single-transform exchange buffer
-constexpr size_t FLOW_SMEM2 = (size_t)FlowSmem<real_t, N, 2>::BYTES;   // two transforms per thread
 constexpr int FLOW_BY_SMEM = (int)(232448 / (FLOW_SMEM + 1024));
 constexpr int FLOW_MINB = FLOW_BY_SMEM < 1 ? 1 : (FLOW_BY_SMEM < TCFD_FLOW_MINB ? FLOW_BY_SMEM : TCFD_FLOW_MINB);
 
@@ -204,7 +203,7 @@ int launch_flow_g(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sm
   static int occ_all[MAX_DEV];
   int& occ = occ_all[cur_dev()];
   auto k = ns2d_flow_kernel<real_t, N, (MAXR > 0 ? MAXR : FLOW_MINB), GR, GC, MODE>;
-  constexpr size_t smem = (MODE & 2) ? FLOW_SMEM2 : FLOW_SMEM;
+  constexpr size_t smem = (MODE & 2) ? (size_t)FlowSmem<real_t, N, 2>::BYTES : FLOW_SMEM;
   int rc = 0;
   if (!occ && (rc = prep(k, smem, NT, &occ))) return rc;
 #ifdef TCFD_EMU
@@ -260,13 +259,14 @@ int launch_flow(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms,
   TCFD_FLOW_CASE(1, 1, 0)
   TCFD_FLOW_CASE(3, 4, 0)
   TCFD_FLOW_CASE(2, 2, MR)
-  if (gr == 3 && gc == 4 && mr == -4) return launch_flow_g<3, 4, MR, 1>(fp, maps, num_sms, stream, win);  // no-FFT timing
-  if (gr == 1 && gc == 1 && mr == -4) return launch_flow_g<1, 1, MR, 1>(fp, maps, num_sms, stream, win);
-  if (gr == 3 && gc == 4 && mr == 32) return launch_flow_g<3, 4, MR, 32>(fp, maps, num_sms, stream, win);  // rolled column loop
-  // two inverse transforms per thread (V = 2)
+  TCFD_FLOW_CASE(1, 1, 5)
+  TCFD_FLOW_CASE(3, 4, 5)
+  TCFD_FLOW_CASE(2, 2, 5)
+  // ping-pong exchange buffers
   if (gr == 3 && gc == 4 && mr == 2) return launch_flow_g<3, 4, MR, 2>(fp, maps, num_sms, stream, win);
   if (gr == 1 && gc == 1 && mr == 2) return launch_flow_g<1, 1, MR, 2>(fp, maps, num_sms, stream, win);
-  if (gr == 3 && gc == 4 && mr == -2) return launch_flow_g<3, 4, MR, 3>(fp, maps, num_sms, stream, win);
+  if (gr == 3 && gc == 4 && mr == -4) return launch_flow_g<3, 4, MR, 1>(fp, maps, num_sms, stream, win);  // no-FFT timing
+  if (gr == 1 && gc == 1 && mr == -4) return launch_flow_g<1, 1, MR, 1>(fp, maps, num_sms, stream, win);
   // cycle attribution per region (fp.prof)
   if (gr == 3 && gc == 4 && mr == -64) return launch_flow_g<3, 4, MR, 64>(fp, maps, num_sms, stream, win);
   if (gr == 1 && gc == 1 && mr == -64) return launch_flow_g<1, 1, MR, 64>(fp, maps, num_sms, stream, win);

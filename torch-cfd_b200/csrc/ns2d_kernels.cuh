@@ -59,7 +59,6 @@ struct NsParams {
   const void* tabU;            // [ND]{lin[NH][2], nil_a[NH], nil_b[NH]}
   const unsigned char* maskU;  // [ND][2][MASK_ROW]
   int in_user, out_user;       // substage reads / writes the reference layout
-  size_t Hplane;               // entries (packed complex) per plane of H2
   int dbg;                     // timing experiments (only with -DTCFD_DEBUG_KNOBS)
   const cx<T>* tw;
   const T* kappa_x;  // [N]   2 pi kx / N^2

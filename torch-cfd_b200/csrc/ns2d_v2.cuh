@@ -8,15 +8,18 @@
 //    each other's global-memory latency;
 //  * the rows kernel works on a DOUBLE item -- the row pairs (2d, N-2d) and (2d+1, N-2d-1) of one
 //    sample in the two lanes -- for the forward y-FFT and the state update, then runs the inverse
-//    y-FFTs of each item with the lanes (u, dw/dx) and (v, dw/dy);
+//    y-FFTs of each item with the lanes (u + i v, dw/dx + i dw/dy): the complex combinations the
+//    column transform packs are formed IN SPECTRAL SPACE (the transforms are linear), one transform
+//    ("P") gives row kx = r1 of z, the other ("Q": u - i v, dw/dx - i dw/dy) conjugated gives row N - r1;
 //  * the cols kernel takes a QUAD of physical columns: per column ONE packed inverse x-FFT carries
-//    all four fields (lane 0: u + i v, lane 1: dw/dx + i dw/dy), the four advection columns go
-//    through ONE packed forward x-FFT; its input tile (128 bytes of each of the N/2+1 rows kx)
-//    arrives by TMA with the 128B swizzle while the previous quad is still being transformed.
+//    all four fields (lane 0: u + i v, lane 1: dw/dx + i dw/dy) and reads its N inputs straight from
+//    the tile (no Hermitian unpacking, every entry read once), the four advection columns go
+//    through ONE packed forward x-FFT; the input tile (64 bytes of each of the N rows kx)
+//    arrives by TMA with the hardware swizzle while the previous quad is still being transformed.
 //
 // Layouts (T = float | double):
-//   H     [B][NH][N][8 T]   entry (kx, y) = { A.x.lo, A.x.hi, A.y.lo, A.y.hi, B.x.lo, ... } with
-//                           A lanes = (u, dw/dx), B lanes = (v, dw/dy) after the y-inverse
+//   H     [B][N][N][4 T]    entry (kx, y) = z = { z1.re, z2.re, z1.im, z2.im }, z1 = u + i v, z2 = dw/dx + i dw/dy
+//                           after the y-inverse (all N rows kx: rows above N/2 hold conj(A) + i conj(B))
 //   advt  [B][ND][N][4 T]   ND = N/4+1 double rows; entry (d, y) = { re_a, re_b, im_a, im_b } of the
 //                           x-transformed advection at rows kx = 2d (a) and 2d+1 (b)
 #pragma once
@@ -86,53 +89,50 @@ TCFD_D cx<L> ns_update2(const NsParams<T>& p, size_t sb, const int (&off)[2], bo
   }
 }
 
-// Two of the four spectra at one entry, in the lanes:  HALF 0 -> (u, dw/dx) = (i ky psi, i kx w),
-// HALF 1 -> (v, dw/dy) = (-i kx psi, i ky w), with psi = nil * w (nil = -1/lap'), kappa = 2 pi k / N^2.
-template <int HALF, class T>
-TCFD_D cx<typename pack2<T>::type> ns_fields2(cx<T> w, T nil, T kx, T ky) {
-  typedef typename pack2<T>::type L;
-  const L s(nil, T(1));
-  const cx<L> q{s * L(w.x), s * L(w.y)};  // lanes (psi, w)
-  const L c = HALF == 0 ? L(ky, kx) : L(-kx, ky);
-  return cx<L>{-(c * q.y), c * q.x};
-}
-
 template <int LANE, class L>
 TCFD_D cx<typename lane_traits<L>::scalar> lane_of(cx<L> v) {
   typedef typename lane_traits<L>::scalar T;
   return LANE ? cx<T>{v.x.hi, v.y.hi} : cx<T>{v.x.lo, v.y.lo};
 }
 
-// y-axis inverse FFT of one half (HALF: lanes (u, dw/dx) or (v, dw/dy)) of the item held in lane
-// LANE of wv (row pair r1, r2 of sample s), written to the H entries of row kx = r1.
-// nil_of(m): -1/laplace' of element m of this item (table in global or shared memory).
-template <int HALF, class T>
-TCFD_D cx<typename pack2<T>::type> ns_fields_s(cx<T> w, T nil, T kx, T ky) {
+// The spectra the packed column transform consumes, formed before the y-inverse (which is linear):
+//   P = A + i B,  Q = A - i B   with lanes  A = (u^, (dw/dx)^) = (i ky psi, i kx w),  B = (v^, (dw/dy)^) = (-i kx psi, i ky w)
+//   =>  P = ( (kx + i ky) psi ,  i (kx + i ky) w ),   Q = ( (-kx + i ky) psi , -i (-kx + i ky) w ),
+// i.e. ONE complex factor (sg kx + i ky) for both lanes applied to q = (psi, sg i w), sg = +1 (P) / -1 (Q);
+// psi = nil * w (nil = -1/lap'), kappa = 2 pi k / N^2.  Row r1 of z is the y-inverse of P completed along ky
+// (entries ky > N/2: conj(Q) of row r2 = N - r1), row r2 is the conjugate of the y-inverse of Q (completed
+// with conj(P) of row r2).
+template <class T>
+TCFD_D cx<typename pack2<T>::type> ns_fields_z(cx<T> w, T nil, T kx, T ky, T sg) {
   typedef typename pack2<T>::type L;
-  const T px = nil * w.x, py = nil * w.y;  // psi
-  if (HALF == 0) return cx<L>{L(-(ky * py), -(kx * w.y)), L(ky * px, kx * w.x)};
-  return cx<L>{L(kx * py, -(ky * w.y)), L(-(kx * px), ky * w.x)};
+  const cx<L> q{L(nil * w.x, -(sg * w.y)), L(nil * w.y, sg * w.x)};  // lanes (psi, sg * i * w)
+  const T a = sg * kx, nky = -ky;
+  return cx<L>{fma_rn(q.x, a, q.y * nky), fma_rn(q.y, a, q.x * ky)};
 }
 
-template <int LANE, int HALF, class T, int N, class L, class Sync, class NilOf>
+// y-axis inverse FFT of one of the two combinations (TYPE 0: P -> row r1 of z, TYPE 1: Q -> row r2) of the
+// item held in lane LANE of wv (row pair r1, r2 of sample s).  nil_of(m): -1/laplace' of element m of this
+// item (table in global or shared memory); nil0 / nilh: the same for columns 0 and N/2.
+template <int LANE, int TYPE, class T, int N, class L, class Sync, class NilOf>
 TCFD_D void rows_inverse_half(const NsParams<T>& p, const cx<L> (&wv)[8], cx<L> e0, cx<L> e1, const T (&kyv)[8],
-                              NilOf nil_of, int r1, int r2, T kx1, T kx2, int s, const FftTwiddles<T, N>& tw,
-                              cx<L>* buf, int& parity, int t, Sync& sync) {
-  constexpr int NT = N / 8, NH = N / 2 + 1;
+                              NilOf nil_of, T nil0, T nilh, int r1, int r2, T kx1, T kx2, int s,
+                              const FftTwiddles<T, N>& tw, cx<L>* buf, int& parity, int t, Sync& sync) {
+  constexpr int NT = N / 8;
+  const T sg = TYPE == 0 ? T(1) : T(-1);
   cx<L> z[1][8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
     const bool lo = m < 4;
-    const cx<L> f = ns_fields_s<HALF, T>(lane_of<LANE>(wv[m]), nil_of(m), lo ? kx1 : kx2, kyv[m]);
+    const cx<L> f = ns_fields_z<T>(lane_of<LANE>(wv[m]), nil_of(m), lo ? kx1 : kx2, kyv[m], lo ? sg : -sg);
     z[0][m] = lo ? f : conj(f);
   }
   if (t == 0) {
     // self-conjugate columns ky = 0 and ky = N/2: Hermitian part of the two rows (C2R semantics)
     const T ky0 = p.kappa_y[0], kyh = p.kappa_y[N / 2];
-    const cx<L> f1 = ns_fields_s<HALF, T>(lane_of<LANE>(wv[0]), p.tab[r1 * NH].nil, kx1, ky0);
-    const cx<L> f2_ = ns_fields_s<HALF, T>(lane_of<LANE>(e0), p.tab[r2 * NH].nil, kx2, ky0);
-    const cx<L> g1 = ns_fields_s<HALF, T>(lane_of<LANE>(e1), p.tab[r1 * NH + N / 2].nil, kx1, kyh);
-    const cx<L> g2 = ns_fields_s<HALF, T>(lane_of<LANE>(wv[4]), p.tab[r2 * NH + N / 2].nil, kx2, kyh);
+    const cx<L> f1 = ns_fields_z<T>(lane_of<LANE>(wv[0]), nil0, kx1, ky0, sg);
+    const cx<L> f2_ = ns_fields_z<T>(lane_of<LANE>(e0), nil0, kx2, ky0, -sg);
+    const cx<L> g1 = ns_fields_z<T>(lane_of<LANE>(e1), nilh, kx1, kyh, sg);
+    const cx<L> g2 = ns_fields_z<T>(lane_of<LANE>(wv[4]), nilh, kx2, kyh, -sg);
     z[0][0] = L(T(0.5)) * (f1 + conj(f2_));
     z[0][4] = L(T(0.5)) * (g1 + conj(g2));
   }
@@ -140,8 +140,8 @@ TCFD_D void rows_inverse_half(const NsParams<T>& p, const cx<L> (&wv)[8], cx<L> 
   if (!(p.dbg & 2))
 #endif
   fft_run<L, N, +1, 1, false, N>(z, tw, buf, parity, t, sync);
-  // plane HALF of H: [sample][kx][y] packed complex -- a warp stores 32 consecutive entries
-  cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + (size_t)HALF * p.Hplane + ((size_t)s * NH + r1) * (size_t)N + t;
+  // row (TYPE ? r2 : r1) of z: [sample][kx][y] packed complex -- a warp stores 32 consecutive entries
+  cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + ((size_t)s * N + (TYPE ? r2 : r1)) * (size_t)N + t;
 #ifdef TCFD_DEBUG_KNOBS
   if (p.dbg & 1) {  // timing experiment: keep the values alive without the H traffic
     T acc = T(0);
@@ -152,7 +152,7 @@ TCFD_D void rows_inverse_half(const NsParams<T>& p, const cx<L> (&wv)[8], cx<L> 
   }
 #endif
 #pragma unroll
-  for (int m = 0; m < 8; ++m) Hrow[m * NT] = z[0][m];
+  for (int m = 0; m < 8; ++m) Hrow[m * NT] = TYPE ? conj(z[0][m]) : z[0][m];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -236,11 +236,14 @@ ns2d_rows2_kernel(const NsParams<T> p) {
     if constexpr (INV) {
       auto nil_a = [&](int m) { return p.tab[m < 4 ? lo_a + m * NT : hi_a - m * NT].nil; };
       auto nil_b = [&](int m) { return p.tab[m < 4 ? lo_b + m * NT : hi_b - m * NT].nil; };
-      rows_inverse_half<0, 0, T, N>(p, wv, e0, e1, kyv, nil_a, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
-      rows_inverse_half<0, 1, T, N>(p, wv, e0, e1, kyv, nil_a, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
+      const T n0a = p.tab[r1a * NH].nil, nha = p.tab[r1a * NH + N / 2].nil;
+      const T n0b = p.tab[r1b * NH].nil, nhb = p.tab[r1b * NH + N / 2].nil;
+      // (self-paired rows kx = 0, N/2: the P transform already gives the row)
+      rows_inverse_half<0, 0, T, N>(p, wv, e0, e1, kyv, nil_a, n0a, nha, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
+      if (!selfa) rows_inverse_half<0, 1, T, N>(p, wv, e0, e1, kyv, nil_a, n0a, nha, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
       if (valid1) {  // CTA-uniform
-        rows_inverse_half<1, 0, T, N>(p, wv, e0, e1, kyv, nil_b, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
-        rows_inverse_half<1, 1, T, N>(p, wv, e0, e1, kyv, nil_b, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
+        rows_inverse_half<1, 0, T, N>(p, wv, e0, e1, kyv, nil_b, n0b, nhb, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
+        if (!selfb) rows_inverse_half<1, 1, T, N>(p, wv, e0, e1, kyv, nil_b, n0b, nhb, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
       }
     }
   }
@@ -436,11 +439,12 @@ ns2d_rows3_kernel(const NsParams<T> p) {
     if constexpr (INV) {
       auto nil_a = [&](int m) { return nilst[m < 4 ? t + m * NT : N - t - m * NT]; };
       auto nil_b = [&](int m) { return nilst[NH + (m < 4 ? t + m * NT : N - t - m * NT)]; };
-      rows_inverse_half<0, 0, T, N>(p, wv, e0, e1, kyv, nil_a, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
-      rows_inverse_half<0, 1, T, N>(p, wv, e0, e1, kyv, nil_a, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
+      const T n0a = nilst[0], nha = nilst[N / 2], n0b = nilst[NH], nhb = nilst[NH + N / 2];
+      rows_inverse_half<0, 0, T, N>(p, wv, e0, e1, kyv, nil_a, n0a, nha, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
+      if (!selfa) rows_inverse_half<0, 1, T, N>(p, wv, e0, e1, kyv, nil_a, n0a, nha, r1a, r2a, kx1a, kx2a, s, tw, buf, parity, t, sync);
       if (valid1) {  // CTA-uniform
-        rows_inverse_half<1, 0, T, N>(p, wv, e0, e1, kyv, nil_b, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
-        rows_inverse_half<1, 1, T, N>(p, wv, e0, e1, kyv, nil_b, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
+        rows_inverse_half<1, 0, T, N>(p, wv, e0, e1, kyv, nil_b, n0b, nhb, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
+        if (!selfb) rows_inverse_half<1, 1, T, N>(p, wv, e0, e1, kyv, nil_b, n0b, nhb, r1b, r2b, kx1b, kx2b, s, tw, buf, parity, t, sync);
       }
     }
     if (unit + 1 < u_end && (unit + 1) / p.B != d) {  // CTA-uniform: the next unit needs another table block
@@ -453,12 +457,12 @@ ns2d_rows3_kernel(const NsParams<T> p) {
 // ------------------------------------------------------------------------------------------
 // cols kernel: CTA = one group, unit = one quad of physical columns of one sample.
 template <class T, class G>
-TCFD_D cx<typename pack2<T>::type> tile_ld(const unsigned char* tile, int row, int plane, int c) {
+TCFD_D cx<typename pack2<T>::type> tile_ld(const unsigned char* tile, int row, int c) {
   typedef typename pack2<T>::type L;
-  if (sizeof(T) == 4) return *reinterpret_cast<const cx<L>*>(tile + G::chunk_offset(row, plane, c));
+  if (sizeof(T) == 4) return *reinterpret_cast<const cx<L>*>(tile + G::chunk_offset(row, c));
   cx<L> r;
-  r.x = *reinterpret_cast<const L*>(tile + G::chunk_offset(row, plane, 2 * c));
-  r.y = *reinterpret_cast<const L*>(tile + G::chunk_offset(row, plane, 2 * c + 1));
+  r.x = *reinterpret_cast<const L*>(tile + G::chunk_offset(row, 2 * c));
+  r.y = *reinterpret_cast<const L*>(tile + G::chunk_offset(row, 2 * c + 1));
   return r;
 }
 
@@ -471,8 +475,8 @@ ns2d_cols2_kernel(const NsParams<T> p, const
                   TileMaps maps) {
   typedef typename pack2<T>::type L;
   constexpr int NT = N / 8, NH = N / 2 + 1, ND = N / 4 + 1;
-  constexpr int IB = 4 * (int)sizeof(cx<L>);  // inner box: 4 columns of one plane (64 or 128 bytes)
-  typedef TileGeom<NH, IB> G;
+  constexpr int IB = 4 * (int)sizeof(cx<L>);  // inner box: 4 columns (64 or 128 bytes)
+  typedef TileGeom<N, IB> G;
   TCFD_DYN_SMEM(smem_raw);
   // hardware swizzle: the tile must start on a 1 KB boundary (offset arithmetic keeps the pointer
   // in the shared address space, so the accesses compile to LDS/STS)
@@ -489,13 +493,12 @@ ns2d_cols2_kernel(const NsParams<T> p, const
 
   auto issue = [&](int j) {  // quad j of this CTA's sequence
     const int quad = (int)blockIdx.x + j * (int)gridDim.x;
-    tile_load_issue<NH, IB>(tile, maps, (quad % (N / 4)) * 4, quad / (N / 4), bar);
+    tile_load_issue<N, IB>(tile, maps, (quad % (N / 4)) * 4, quad / (N / 4), bar);
   };
 #ifndef TCFD_EMU
   if (t == 0) {
     mbar_init(bar, 1);
     tma_prefetch_desc(&maps.main);
-    tma_prefetch_desc(&maps.last);
   }
 #endif
   __syncthreads();
@@ -512,15 +515,7 @@ ns2d_cols2_kernel(const NsParams<T> p, const
     for (int c = 0; c < 4; ++c) {
       cx<L> z[1][8];
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int k = t + m * NT;
-        const bool lo = (m < 4) || (m == 4 && t == 0);  // k <= N/2
-        const int row = lo ? k : N - k;
-        const cx<L> A = tile_ld<T, G>(tile, row, 0, c);
-        const cx<L> Bv = tile_ld<T, G>(tile, row, 1, c);
-        z[0][m] = lo ? cx<L>{A.x - Bv.y, A.y + Bv.x} : cx<L>{A.x + Bv.y, Bv.x - A.y};
-        if ((m == 0 || m == 4) && t == 0) z[0][m] = cx<L>{A.x, Bv.x};  // kx = 0, N/2: real rows
-      }
+      for (int m = 0; m < 8; ++m) z[0][m] = tile_ld<T, G>(tile, t + m * NT, c);
       fft_run<L, N, +1, 1, false, N>(z, tw, buf, parity, t, sync);
       if (c == 3) {
         // every thread has passed a barrier after consuming its tile reads: the tile is free

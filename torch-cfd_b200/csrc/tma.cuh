@@ -11,38 +11,34 @@
 
 namespace tcfd {
 
-// The H tile source.  H is stored as two planes (A: lanes (u, dw/dx), B: lanes (v, dw/dy)), each
-// [sample][kx][y] entries of one packed complex (ENT bytes).  A tile is, for every row kx of one
-// sample, the 4 entries of 4 consecutive columns y in both planes.
+// The H tile source.  H holds, per sample, the N x N array z[kx][y] of packed complex entries (ENT bytes):
+// lanes (u + i v, dw/dx + i dw/dy) after the y-inverse -- i.e. exactly the input of the packed x-axis
+// inverse transform of column y (rows kx > N/2 are written by the rows units as conjugates, so the column
+// kernel reads every entry once and does no Hermitian unpacking).  A tile is, for every row kx of one
+// sample, the 4 entries of 4 consecutive columns y.
 #ifndef TCFD_EMU
 struct alignas(64) TileMaps {
-  CUtensorMap main;  // rank 4, box {4 entries, min(256, NH-1) rows, 1 sample, 2 planes}
-  CUtensorMap last;  // rank 4, box {4 entries, 1 row, 1 sample, 2 planes}: the Nyquist row kx = N/2
+  CUtensorMap main;  // rank 3, box {4 entries, min(256, N) rows, 1 sample}
 };
 #else
 struct TileMaps {
   const unsigned char* base;
-  size_t row_bytes, sample_bytes, plane_bytes;
+  size_t row_bytes, sample_bytes;
 };
 #endif
 
-// Shared-memory image of a tile with NH rows whose inner box is IB = 64 or 128 bytes (hardware
-// swizzle of the same width).  Rows [0, NH-1) arrive in boxes of BOX rows x 2 planes, stored
-// [box][plane][row][IB]; the last row's two planes follow.  tile_entry_offset returns the byte
-// offset of 16-byte chunk j of (row, plane) -- the swizzle XORs the chunk index with address bits
-// 7.. (the tile base is 1 KB aligned, so offsets and addresses agree in those bits).
-template <int NH, int IB>
+// Shared-memory image of a tile with NR rows whose inner box is IB = 64 or 128 bytes (hardware swizzle of
+// the same width).  The rows arrive in boxes of BOX rows, stored [box][row][IB] (i.e. row-major).
+// chunk_offset returns the byte offset of 16-byte chunk j of a row -- the swizzle XORs the chunk index with
+// address bits 7.. (the tile base is 1 KB aligned, so offsets and addresses agree in those bits).
+template <int NR, int IB>
 struct TileGeom {
-  static constexpr int BOX = (NH - 1) < 256 ? (NH - 1) : 256;
-  static constexpr int NBOX = (NH - 1) / BOX;
-  static constexpr int BYTES = ((NH * 2 * IB) + 1023) / 1024 * 1024;
+  static constexpr int BOX = NR < 256 ? NR : 256;
+  static constexpr int NBOX = NR / BOX;
+  static constexpr int BYTES = ((NR * IB) + 1023) / 1024 * 1024;
   static constexpr int XMASK = IB / 16 - 1;  // 3 (64B swizzle) or 7 (128B swizzle)
-  TCFD_HD static int row_offset(int row, int plane) {
-    if (row < NH - 1) return ((row / BOX) * 2 + plane) * (BOX * IB) + (row % BOX) * IB;
-    return NBOX * 2 * BOX * IB + plane * IB;
-  }
-  TCFD_HD static int chunk_offset(int row, int plane, int j) {
-    const int ro = row_offset(row, plane);
+  TCFD_HD static int chunk_offset(int row, int j) {
+    const int ro = row * IB;
     return ro + ((j ^ ((ro >> 7) & XMASK)) << 4);
   }
 };
@@ -158,27 +154,22 @@ TCFD_D void stage_barrier_init(unsigned long long* bar) {
 #endif
 }
 
-// Issue the load of one tile (called by ONE thread): columns y0..y0+3 of `sample`.
-// elems_per_entry = reals per packed complex entry (4).
-template <int NH, int IB>
+// Issue the load of one tile (called by ONE thread): columns y0..y0+3 of `sample`, all NR rows.
+template <int NR, int IB>
 TCFD_D void tile_load_issue(unsigned char* tile, const TileMaps& maps, int y0, int sample, unsigned long long* bar) {
-  typedef TileGeom<NH, IB> G;
+  typedef TileGeom<NR, IB> G;
 #ifndef TCFD_EMU
-  mbar_expect_tx(bar, (unsigned)NH * 2u * (unsigned)IB);
+  mbar_expect_tx(bar, (unsigned)NR * (unsigned)IB);
   const int c0 = y0 * 4;  // innermost coordinate in reals: 4 reals per entry
 #pragma unroll
-  for (int b = 0; b < G::NBOX; ++b)
-    tma_load_4d(tile + b * 2 * G::BOX * IB, &maps.main, c0, b * G::BOX, sample, 0, bar);
-  tma_load_4d(tile + G::NBOX * 2 * G::BOX * IB, &maps.last, c0, NH - 1, sample, 0, bar);
+  for (int b = 0; b < G::NBOX; ++b) tma_load_3d(tile + b * G::BOX * IB, &maps.main, c0, b * G::BOX, sample, bar);
 #else
   (void)bar;
   const int ent = IB / 4;  // bytes per entry
-  for (int pl = 0; pl < 2; ++pl)
-    for (int r = 0; r < NH; ++r) {
-      const unsigned char* src = maps.base + (size_t)pl * maps.plane_bytes + (size_t)sample * maps.sample_bytes +
-                                 (size_t)r * maps.row_bytes + (size_t)y0 * ent;
-      for (int j = 0; j < IB / 16; ++j) std::memcpy(tile + G::chunk_offset(r, pl, j), src + 16 * j, 16);
-    }
+  for (int r = 0; r < NR; ++r) {
+    const unsigned char* src = maps.base + (size_t)sample * maps.sample_bytes + (size_t)r * maps.row_bytes + (size_t)y0 * ent;
+    for (int j = 0; j < IB / 16; ++j) std::memcpy(tile + G::chunk_offset(r, j), src + 16 * j, 16);
+  }
 #endif
 }
 
