@@ -46,13 +46,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ns2d", choices=["ns2d", "sconv_c4", "fno3d_c5"],
+                    help="ns2d: the headline RK4+CN step (default); sconv_c4 / fno3d_c5: BASELINE configs[3] / [4] of hot path B")
+    ap.add_argument("--width", type=int, default=20, help="path B: channel width")
     ap.add_argument("--n", type=int, default=512)
-    ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (ns2d: 64, sconv_c4: 32); fno3d_c5: GLOBAL batch (128)")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = {"ns2d": 64, "sconv_c4": 32, "fno3d_c5": 128}[a.workload]
+    return a
 
 
 def peaks():
@@ -336,6 +342,304 @@ def run_ours(a):
     _emit(json.dumps(out))
 
 
+# ================================================================================================
+# hot path B workloads (BASELINE.json configs[3] "C4" and configs[4] "C5"), same JSON schema
+def _dist_setup():
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return x
+
+    def finish():
+        if world > 1:
+            dist.destroy_process_group()
+    return world, rank, local, dev, barrier, max_over_ranks, finish
+
+
+def _timed(fn, K, W, barrier, max_over_ranks, local):
+    for _ in range(W):
+        fn()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        fn()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    return ms, sampler.stop()
+
+
+C4 = dict(X=256, Y=256, T=10, modes=(20, 20, 8))  # SpectralConvT(temporal_padding=True): 10 -> 20 samples, 11 t-frequencies
+
+
+def sconv_workload_name(b, C):
+    return (f"SFNO spectral conv forward+backward, SpectralConvT(temporal_padding) x = ({b}, {C}, 256, 256, 10) per GPU, "
+            f"modes (20, 20, 8), fp32")
+
+
+def sconv_alg_bytes(b, C):
+    act = b * C * C4["X"] * C4["Y"] * C4["T"] * 4
+    wbytes = 4 * C * C * 20 * 20 * 8 * 8
+    return 2 * act + wbytes, 4 * act + 3 * wbytes  # forward, forward + backward
+
+
+def sconv_cpu(b, C, threads, batch_sample):
+    """Oracle (reference arithmetic, torch CPU) forward + backward of a reduced batch, scaled to b."""
+    from oracle import sconv_oracle as SO
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    x = torch.randn(batch_sample, C, C4["X"], C4["Y"], C4["T"], requires_grad=True)
+    w = [(0.5 / (C * C) * torch.rand(C, C, 20, 20, 8, 2)).requires_grad_() for _ in range(4)]
+    cot = torch.randn(batch_sample, C, C4["X"], C4["Y"], C4["T"])
+
+    def step():
+        y = SO.spectral_conv_t(x, w, 20, 20, 8, C4["T"], None, 0.1, True)
+        y.backward(cot)
+        x.grad = None
+    step()
+    t0 = time.perf_counter()
+    step()
+    el = (time.perf_counter() - t0) * b / batch_sample
+    return 1.0 / el, el
+
+
+def run_sconv(a):
+    from torch_cfd_b200.fno import SpectralConvT
+    world, rank, local, dev, barrier, max_over_ranks, finish = _dist_setup()
+    b, C, K, W = a.batch, a.width, a.steps, max(3, a.warmup)
+    torch.manual_seed(rank)
+    m = SpectralConvT(C, C, 20, 20, 8, out_steps=C4["T"], temporal_padding=True, bias=False).to(dev)
+    x_host = torch.randn(b, C, C4["X"], C4["Y"], C4["T"]).pin_memory()
+    cot_host = torch.randn(b, C, C4["X"], C4["Y"], C4["T"]).pin_memory()
+    x = x_host.to(dev).requires_grad_()
+    cot = cot_host.to(dev)
+    plan_launches = [0]
+
+    def fwdbwd():
+        y = m(x)
+        y.backward(cot)
+        plan_launches[0] += sum(p.last_launch_count for p in m._cache._plans.values())
+        x.grad = None
+        for p in m.parameters():
+            p.grad = None
+
+    def fwd():
+        with torch.no_grad():
+            m(x)
+    ms, clocks = _timed(fwdbwd, K, W, barrier, max_over_ranks, local)
+    launches = plan_launches[0] * K // (K + W)
+    ms_f, _ = _timed(fwd, K, W, barrier, max_over_ranks, local)
+    # end to end: pinned host x and cotangent up, forward + backward, y and grad_x down, every step
+    y_host, gx_host = torch.empty_like(x_host), torch.empty_like(x_host)
+    e2e = None
+    if not a.no_e2e:
+        Ke = max(3, min(K, 10))
+
+        def step_host():
+            xd = x_host.to(dev, non_blocking=True).requires_grad_()
+            cd = cot_host.to(dev, non_blocking=True)
+            y = m(xd)
+            y.backward(cd)
+            y_host.copy_(y.detach(), non_blocking=True)
+            gx_host.copy_(xd.grad, non_blocking=True)
+            for p in m.parameters():
+                p.grad = None
+            torch.cuda.current_stream().synchronize()
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            step_host()
+        barrier()
+        el = max_over_ranks(time.perf_counter() - t0)
+        nb = x_host.numel() * 4
+        e2e = {"value": world * Ke / el, "unit": UNIT, "h2d_bytes_per_step": 2 * nb, "d2h_bytes_per_step": 2 * nb, "steps": Ke}
+    finish()
+    if rank != 0:
+        return
+    alg_f, alg_fb = sconv_alg_bytes(b, C)
+    peak, peak_src = peaks()
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["sconv_c4"]["dram_bytes_fwd_bwd"]
+    except (OSError, KeyError, ValueError):
+        pass
+    out = {
+        "metric": "sconv_fwd_bwd_steps_per_sec", "value": world * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": sconv_workload_name(b, C), "step": "one forward + backward of the layer on every GPU",
+                   "reading": "BASELINE configs[3] with modes_t = 8 needs >= 8 t-frequencies: T = 10 is zero-padded to 20 "
+                              "(SpectralConvT temporal_padding, the SFNO OutConv path), SURVEY 8d",
+                   "l2": f"activations {x_host.numel() * 4 / 1e6:.0f} MB per tensor exceed the 126 MB L2; no flush",
+                   "ms_forward_only": ms_f / K},
+        "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": "tcfd_sconv3d forward + backward (all launches of the step)",
+                     "achieved": alg_fb / (ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg_fb / (ms / K * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": alg_fb,
+                     "forward_only": {"achieved": alg_f / (ms_f / K * 1e-3) / 1e9, "frac": alg_f / (ms_f / K * 1e-3) / 1e9 / peak,
+                                      "algorithmic_bytes": alg_f}},
+    }
+    if not a.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        v, el = sconv_cpu(b, C, threads, 1)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"forward + backward of 1 sample of the batch (oracle, torch CPU), scaled x{b}"}
+    _emit(json.dumps(out))
+
+
+def run_sconv_reference(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    nb = max(1, min(a.batch, 2))
+    v, el = sconv_cpu(a.batch, a.width, threads, nb)
+    sample = f"forward + backward of {nb} samples of the batch (oracle port, torch CPU, {threads} threads), scaled to {a.batch}"
+    _emit(json.dumps({
+        "impl": "reference", "metric": "sconv_fwd_bwd_steps_per_sec", "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": 1,
+        "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": sconv_workload_name(a.batch, a.width), "note": "CPU arm: rank 0 only"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+C5 = dict(X=128, Y=128, T=10, modes=(8, 8, 5), in_ch=13)
+
+
+def fno3d_workload_name(batch, C):
+    return f"FNO3d(8, 8, 5, width={C}) full forward (4 spectral layers), x = ({batch}, 13, 128, 128, 10) fp32 GLOBAL batch"
+
+
+def fno3d_cpu(batch, C, threads, nb):
+    """The reference's layer sequence with torch CPU ops (spectral conv = oracle) on nb samples, scaled."""
+    from oracle import sconv_oracle as SO
+    import torch.nn as nn
+    import torch.nn.functional as F
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    x = torch.randn(nb, C5["in_ch"], C5["X"], C5["Y"], C5["T"])
+    p = nn.Conv3d(13, C, 1)
+    layers = [([torch.rand(C, C, 8, 8, 5, dtype=torch.cfloat) / (C * C) for _ in range(4)],
+               nn.Conv3d(C, C, 1), nn.Conv3d(C, C, 1), nn.Conv3d(C, C, 1)) for _ in range(4)]
+    q1, q2 = nn.Conv3d(C, 128, 1), nn.Conv3d(128, 1, 1)
+
+    def fwd():
+        with torch.no_grad():
+            h = p(x)
+            for k, (w, m1, m2, ww) in enumerate(layers):
+                h2 = m2(F.gelu(m1(SO.spectral_conv3d(h, w, 8, 8, 5)))) + ww(h)
+                h = F.gelu(h2) if k < 3 else h2
+            return q2(q1(h))
+    fwd()
+    t0 = time.perf_counter()
+    fwd()
+    el = (time.perf_counter() - t0) * batch / nb
+    return 1.0 / el, el
+
+
+def run_fno3d(a):
+    from torch_cfd_b200.fno import FNO3d
+    world, rank, local, dev, barrier, max_over_ranks, finish = _dist_setup()
+    B, C, K, W = a.batch, a.width, a.steps, max(3, a.warmup)
+    b = B // world
+    torch.manual_seed(0)
+    m = FNO3d(8, 8, 5, C, input_channel=10).to(dev).eval()
+    x_host = torch.randn(b, 13, C5["X"], C5["Y"], C5["T"]).pin_memory()
+    x = x_host.to(dev)
+
+    def fwd():
+        with torch.no_grad():
+            m(x)
+    ms, clocks = _timed(fwd, K, W, barrier, max_over_ranks, local)
+    e2e = None
+    if not a.no_e2e:
+        Ke = max(3, min(K, 10))
+        y_host = torch.empty(b, C5["X"], C5["Y"], C5["T"]).pin_memory()
+
+        def step_host():
+            with torch.no_grad():
+                y, _ = m(x_host.to(dev, non_blocking=True))
+                y_host.copy_(y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            step_host()
+        barrier()
+        el = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": Ke / el, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4,
+               "steps": Ke}
+    finish()
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    act = b * C * C5["X"] * C5["Y"] * C5["T"] * 4
+    # algorithmic bytes of ONE forward per GPU with the glue fused: lifting reads 13/C + writes 1, every layer reads h
+    # twice (conv, skip) + conv output written and read once + layer output written, projection reads 1 (+ 1/C out)
+    alg = act * (13.0 / C + 1) + 4 * act * 5 + act * (1 + 1.0 / C)
+    # launches per forward: lifting 1 + 4 x (5 spectral-conv kernels + 1 glue) + projection 1
+    out = {
+        "metric": "fno3d_forward_steps_per_sec", "value": K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": fno3d_workload_name(B, C), "step": f"one forward of the GLOBAL batch {B}, sharded {b} per GPU",
+                   "samples_per_s": B * K / (ms * 1e-3),
+                   "l2": f"activations {act / 1e6:.0f} MB per tensor per GPU exceed the 126 MB L2 up to 4 GPUs; no flush"},
+        "clocks": clocks, "gpu_launches": K * (1 + 4 * 6 + 1), "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": "whole forward (lifting, 4 x [spectral conv + fused layer glue], projection)",
+                     "achieved": alg / (ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (ms / K * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": alg,
+                     "note": "bytes of the fused design: every activation tensor read / written once per consumer"},
+    }
+    if not a.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        v, el = fno3d_cpu(B, C, threads, 2)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"forward of 2 samples (reference layer sequence, torch CPU), scaled x{B // 2}"}
+    _emit(json.dumps(out))
+
+
+def run_fno3d_reference(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    v, el = fno3d_cpu(a.batch, a.width, threads, 4)
+    sample = f"forward of 4 samples (reference layer sequence, torch CPU, {threads} threads), scaled to {a.batch}"
+    _emit(json.dumps({
+        "impl": "reference", "metric": "fno3d_forward_steps_per_sec", "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": 1,
+        "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": fno3d_workload_name(a.batch, a.width), "note": "CPU arm: rank 0 only"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 def _emit(line: str):
     os.write(_REAL_STDOUT, (line + "\n").encode())
 
@@ -347,7 +651,7 @@ if __name__ == "__main__":
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    table = {("ns2d", "ours"): run_ours, ("ns2d", "reference"): run_reference,
+             ("sconv_c4", "ours"): run_sconv, ("sconv_c4", "reference"): run_sconv_reference,
+             ("fno3d_c5", "ours"): run_fno3d, ("fno3d_c5", "reference"): run_fno3d_reference}
+    table[(args.workload, args.impl)](args)

@@ -167,6 +167,22 @@ int tcfd_sconv3d_backward(tcfd_sconv3d_t* h, const void* grad_y, const void* xha
                           void* grad_x, void* const* grad_w, void* const* grad_bias, float delta, int batch,
                           void* stream);
 
+/* The two halves of the layer as separate calls, for callers that put something between them in spectral
+ * space: SpectralConvT's `postprocess` (HelmholtzProjection, fno/sfno.py:116-193, :452) or a change of mesh
+ * (SpectralConv.forward with out_mesh_size, fno/base.py:229-237 -- the synthesis then runs on the handle of the
+ * output geometry).  yhat = the truncated output spectrum [batch][Co][2mx][2my][mt] complex64 (kx rows: the mx
+ * lowest then the mx highest frequencies, likewise ky), in the layer's normalisation:
+ *   forward  == synthesis(analysis(x));  backward == analysis_backward(synthesis_backward(grad_y)).
+ * grad_yhat follows torch's convention for gradients of complex tensors. */
+size_t tcfd_sconv3d_yhat_elems(const tcfd_sconv3d_t* h, int batch);
+int tcfd_sconv3d_analysis(tcfd_sconv3d_t* h, const void* x, const void* const* w, const void* const* bias, float delta,
+                          void* yhat, void* xhat_save, int batch, void* stream);
+int tcfd_sconv3d_synthesis(tcfd_sconv3d_t* h, const void* yhat, void* y, int batch, void* stream);
+int tcfd_sconv3d_synthesis_backward(tcfd_sconv3d_t* h, const void* grad_y, void* grad_yhat, int batch, void* stream);
+int tcfd_sconv3d_analysis_backward(tcfd_sconv3d_t* h, const void* grad_yhat, const void* xhat, const void* const* w,
+                                   void* grad_x, void* const* grad_w, void* const* grad_bias, float delta, int batch,
+                                   void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * FNO3d layer glue: the pointwise channel mixes around the spectral convolution,
  * inference only, fp32, tensors (batch, C, X, Y, T) contiguous with npts = X*Y*T points per channel plane.
@@ -187,6 +203,28 @@ int tcfd_fno_layer_glue(const float* conv_out, const float* x, float* y, const f
                         size_t npts, void* stream);
 int tcfd_fno_project(const float* x, float* y, const float* w1, const float* b1, const float* w2, const float* b2,
                      int act, int batch, int C, int M, size_t npts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone batched 2-D real transforms and the bilinear resampling of the data-generation scripts
+ * (post-processing of recorded trajectories on the device; also the forcing spectra and
+ * initial-condition generators).  Layouts as above: spectrum [count][n][n/2+1] complex, field [count][n][n]
+ * real, precision of the handle, "backward" normalisation.
+ *   tcfd_fft2_irfft2         torch.fft.irfft2(value)    (fno/data_gen/data_gen_Kolmogorov2d.py:178-179,
+ *                            data_gen_McWilliams2d.py:157): C2R semantics included (imaginary parts of the
+ *                            ky = 0, n/2 bins are dropped after the kx transform)
+ *   tcfd_fft2_rfft2          torch.fft.rfft2(field)     (torch_cfd/equations.py:432-436)
+ *   tcfd_resample_bilinear   F.interpolate(value, size=(n_out, n_out), mode="bilinear")
+ *                            (fno/data_gen/data_gen_Kolmogorov2d.py:186, align_corners=False) with the cast
+ *                            `.to(dtype)` of :179 folded in (prec_in -> prec_out)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tcfd_fft2 tcfd_fft2_t;
+int tcfd_fft2_create(tcfd_fft2_t** out, int n, int prec);
+int tcfd_fft2_destroy(tcfd_fft2_t* h);
+int tcfd_fft2_last_launch_count(const tcfd_fft2_t* h);
+int tcfd_fft2_irfft2(tcfd_fft2_t* h, const void* in_hat, void* out, int count, void* stream);
+int tcfd_fft2_rfft2(tcfd_fft2_t* h, const void* in, void* out_hat, int count, void* stream);
+int tcfd_resample_bilinear(const void* in, void* out, int prec_in, int prec_out, int count, int n_in, int n_out,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -254,7 +254,58 @@ def sconv_cases(grid32=False):
     np.savez_compressed(os.path.join(HERE, "sconv.npz"), **out)
 
 
+def sfno_case():
+    """sfno.npz: the x / y change of mesh of SpectralConv.forward (fno/base.py:229-237), SpectralConvT with the
+    HelmholtzProjection post-process (fno/sfno.py:116-193, :452) -- values and all gradients -- and a small SFNO
+    (fno/sfno.py:460-620): its state_dict, an input and the outputs for two output lengths."""
+    torch.set_default_dtype(torch.float32)
+    from fno.sfno import SFNO, HelmholtzProjection, SpectralConvS, SpectralConvT
+    out = {}
+
+    def run(tag, mod, x, **fw):
+        x = x.clone().requires_grad_(True)
+        y = mod(x, **fw)
+        cot = torch.randn(y.shape, generator=torch.Generator().manual_seed(123))
+        (y * cot).sum().backward()
+        for k, v in (("x", x), ("y", y), ("cot", cot), ("gx", x.grad)):
+            out[f"{tag}_{k}"] = _np(v)
+        for pname, p in mod.named_parameters():
+            key = pname.replace(".", "_")
+            out[f"{tag}_p_{key}"] = _np(p)
+            out[f"{tag}_g_{key}"] = _np(p.grad)
+        print(tag, tuple(x.shape), "->", tuple(y.shape))
+
+    torch.manual_seed(5)
+    m = SpectralConvS(2, 2, 4, 4, 3)
+    run("cs_up", m, torch.randn(1, 2, 32, 32, 8), out_mesh_size=[64, 64, 12])
+    m = SpectralConvS(2, 3, 6, 5, 3, norm="ortho")
+    run("cs_down", m, torch.randn(2, 2, 64, 64, 8), out_mesh_size=[32, 32, 6])
+    m = SpectralConvT(2, 2, 4, 4, 3, out_steps=6, temporal_padding=True, bias=True,
+                      postprocess=HelmholtzProjection(n_grid=32, diam=1))
+    with torch.no_grad():
+        for b in m.bias:
+            b.copy_(torch.randn_like(b))
+    run("ct_helm", m, torch.randn(2, 2, 32, 32, 5))
+    torch.manual_seed(6)
+    model = SFNO(4, 4, 3, 8, num_spectral_layers=3, latent_steps=5)
+    with torch.no_grad():
+        for b in model.output_operator.conv.bias:
+            b.copy_(0.1 * torch.randn_like(b))
+    x = torch.randn(2, 32, 32, 6)
+    with torch.no_grad():
+        out["sfno_x"] = _np(x)
+        out["sfno_y"] = _np(model(x))
+        out["sfno_y9"] = _np(model(x, out_steps=9))
+    for k, v in model.state_dict().items():
+        out[f"sfno_sd_{k}"] = _np(v)
+    print("sfno", tuple(x.shape), "->", out["sfno_y"].shape, out["sfno_y9"].shape, len(model.state_dict()), "state_dict entries")
+    np.savez_compressed(os.path.join(HERE, "sfno.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sfno":
+        sfno_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "signatures":
         signature_case()
         sys.exit(0)
@@ -280,3 +331,4 @@ if __name__ == "__main__":
     imex_case()
     sconv_cases()
     sconv_cases(grid32=True)
+    sfno_case()

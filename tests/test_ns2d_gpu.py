@@ -397,3 +397,78 @@ def test_staged_device_to_host_copy_equals_cpu():
     finally:
         solvers._RING_BYTES = old
         solvers._RING.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+# post-processing of recorded trajectories on the device; A7: state-dependent forcing
+@pytest.mark.parametrize("n,dtype,tol", [(64, torch.float64, 1e-13), (256, torch.float32, 2e-6), (512, torch.float32, 2e-6),
+                                         (1024, torch.float32, 3e-6)])
+def test_fft2_vs_torch(n, dtype, tol):
+    import torch_cfd_b200 as T
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(3, n, n, generator=g, dtype=dtype)
+    xh = T.fft.rfft2(x.to(DEV))
+    assert rel_l2(xh, torch.fft.rfft2(x)) < tol
+    cd = xh.dtype
+    yh = (torch.randn(2, 2, n, n // 2 + 1, generator=g, dtype=dtype) + 1j * torch.randn(2, 2, n, n // 2 + 1, generator=g, dtype=dtype)).to(cd)
+    y = T.fft.irfft2(yh.to(DEV))  # non-Hermitian input: C2R semantics
+    ref = torch.fft.irfft2(yh)
+    assert y.shape == ref.shape and y.dtype == ref.dtype and rel_l2(y, ref) < tol
+    assert rel_l2(T.fft.irfft2(xh), x) < 2 * tol
+
+
+def test_postprocess_trajectory_vs_reference_ops():
+    """fno/data_gen/data_gen_Kolmogorov2d.py:178-188: irfft2 -> .real.cpu().to(dtype) -> F.interpolate(bilinear),
+    here on the device before the copy; compared with the same torch CPU ops on the same recorded spectra."""
+    import torch.nn.functional as F
+    import torch_cfd_b200 as T
+    n, dtype = 256, torch.float32
+    with default_dtype(dtype):
+        ns = build_module(n, dtype, 1e-3, 0.1, "vorticity")
+        w0 = O.synthetic_vorticity_hat(n, 3, 11, dtype)
+        dev = T.get_trajectory_imex(ns, w0.to(DEV), 1e-3, num_steps=6, record_every_steps=2, device_result=True)
+        for sub in (1, 4):
+            out = T.postprocess_trajectory(dev, subsample=sub, dtype=torch.float32)
+            for k, v in dev.items():
+                ref = torch.fft.irfft2(v.cpu()).real.to(torch.float32)
+                if sub > 1:
+                    ref = F.interpolate(ref, size=(n // sub, n // sub), mode="bilinear")
+                assert out[k].shape == ref.shape and out[k].dtype == ref.dtype and not out[k].is_cuda
+                assert (out[k] - ref).abs().max().item() < 3e-6 * ref.abs().max().item(), (k, sub)
+
+
+def test_state_dependent_forcing_host_loop():
+    """A user forcing that reads its state (torch_cfd/equations.py:429-437 allows it) takes the per-sub-stage
+    host loop: CUDA advection + forcing evaluated from the state with the libtcfd transforms."""
+    import torch_cfd_b200 as T
+    n, dtype = 64, torch.float64
+    with default_dtype(dtype):
+        diam = 2 * torch.pi
+        grid = T.Grid(shape=(n, n), domain=((0, diam), (0, diam)))
+
+        class Damp:  # vorticity-form forcing -0.3 * w(x, y)
+            vorticity = True
+
+            def __call__(self, grid, w_hat):
+                if w_hat is None:
+                    raise RuntimeError("state-dependent")
+                return -0.3 * (torch.fft.irfft2(w_hat.cpu()) if not w_hat.is_cuda else T.fft.irfft2(w_hat))
+
+        ns = T.NavierStokes2DSpectral(viscosity=1e-3, grid=grid, drag=0.0, smooth=True, forcing_fn=Damp(),
+                                      solver=T.RK4CrankNicolsonStepper()).to(DEV)
+        assert ns.state_dependent_forcing
+        w0 = O.synthetic_vorticity_hat(n, 2, 3, dtype)
+        w, dwdt = ns(w0.to(DEV), 1e-3, steps=3)
+        # oracle: the unforced tables + the same forcing added to F in every sub-stage
+        tb = oracle_tables(n, dtype, 1e-3, 0.0, None)
+        a, b, g = O.rk_coefficients(True, dtype)
+        u = w0.clone()
+        for _ in range(3):
+            h = 0
+            for k in range(len(b)):
+                F_ = O.explicit_terms(tb, u) + torch.fft.rfft2(-0.3 * torch.fft.irfft2(u))
+                h = F_ + b[k] * h
+                mu = 0.5 * 1e-3 * (a[k + 1] - a[k])
+                u = O.implicit_solve(tb, u + g[k] * 1e-3 * h + mu * O.implicit_terms(tb, u), mu)
+        assert rel_l2(w, u) < 1e-11
+        assert rel_l2(dwdt, (u - w0) / 3e-3) < 1e-7

@@ -103,3 +103,44 @@ def test_sconv_modules_mirror_reference_parameters():
     assert t.delta == 1e-1 and t.bias is not False and t.out_steps == 5
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 3, 32, 32, 8))
+
+
+def test_emu_two_halves_equal_the_fused_call():
+    """tcfd_sconv3d_analysis + tcfd_sconv3d_synthesis == tcfd_sconv3d_forward, and the two adjoints compose to
+    tcfd_sconv3d_backward (the split used for a spectral post-process / a change of mesh)."""
+    torch.manual_seed(7)
+    b, Ci, Co, X, Y, T, mx, my, mt = 2, 2, 3, 32, 32, 6, 4, 5, 3
+    plan = _emu_plan((X, Y, T, 0, T, Ci, Co, mx, my, mt, "backward"), b)
+    x = torch.randn(b, Ci, X, Y, T)
+    w = [torch.view_as_complex((0.1 * torch.randn(Ci, Co, mx, my, mt, 2)).contiguous()) for _ in range(4)]
+    y = torch.empty(b, Co, X, Y, T)
+    xhat = torch.empty(plan.xhat_elems(b), dtype=torch.complex64)
+    plan.forward(x, w, None, 1.0, y, xhat)
+    yhat = torch.empty(plan.yhat_shape(b), dtype=torch.complex64)
+    xhat2 = torch.empty_like(xhat)
+    plan.analysis(x, w, None, 1.0, yhat, xhat2)
+    y2 = torch.empty_like(y)
+    plan.synthesis(yhat, y2)
+    assert torch.equal(y, y2) and torch.equal(xhat, xhat2)
+    cot = torch.randn_like(y)
+    gx, gw = torch.empty_like(x), [torch.empty_like(t) for t in w]
+    plan.backward(cot, xhat, w, gx, gw, None, 1.0)
+    gyhat = torch.empty_like(yhat)
+    plan.synthesis_backward(cot, gyhat)
+    gx2, gw2 = torch.empty_like(x), [torch.empty_like(t) for t in w]
+    plan.analysis_backward(gyhat, xhat, w, gx2, gw2, None, 1.0)
+    assert torch.equal(gx, gx2) and all(torch.equal(a, c) for a, c in zip(gw, gw2))
+    # <synthesis(yhat), cot> == Re <yhat, synthesis_backward(cot)>  (torch's convention for complex gradients)
+    lhs = float((y2.double() * cot.double()).sum())
+    rhs = float((yhat.to(torch.complex128).conj() * gyhat.to(torch.complex128)).real.sum())
+    assert abs(lhs - rhs) < 1e-4 * abs(lhs)
+
+
+def test_sfno_shim_state_dict_matches_reference():
+    """Keys and shapes of the SFNO shim == those of the reference model the fixture was generated from."""
+    from torch_cfd_b200.fno import SFNO
+    g = load_golden("sfno")
+    model = SFNO(4, 4, 3, 8, num_spectral_layers=3, latent_steps=5)
+    ref = {k[len("sfno_sd_"):]: g[k].shape for k in g.files if k.startswith("sfno_sd_")}
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == {k: tuple(v) for k, v in ref.items()}

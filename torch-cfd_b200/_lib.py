@@ -79,6 +79,18 @@ class TcfdLibrary:
         c.tcfd_sconv3d_last_launch_count.argtypes = [vp]
         c.tcfd_sconv3d_forward.argtypes = [vp, vp, pp, pp, ctypes.c_float, vp, vp, ci, vp]
         c.tcfd_sconv3d_backward.argtypes = [vp, vp, vp, pp, vp, pp, pp, ctypes.c_float, ci, vp]
+        c.tcfd_sconv3d_yhat_elems.argtypes = [vp, ci]
+        c.tcfd_sconv3d_yhat_elems.restype = ctypes.c_size_t
+        c.tcfd_sconv3d_analysis.argtypes = [vp, vp, pp, pp, ctypes.c_float, vp, vp, ci, vp]
+        c.tcfd_sconv3d_synthesis.argtypes = [vp, vp, vp, ci, vp]
+        c.tcfd_sconv3d_synthesis_backward.argtypes = [vp, vp, vp, ci, vp]
+        c.tcfd_sconv3d_analysis_backward.argtypes = [vp, vp, vp, pp, vp, pp, pp, ctypes.c_float, ci, vp]
+        c.tcfd_fft2_create.argtypes = [ctypes.POINTER(vp), ci, ci]
+        c.tcfd_fft2_destroy.argtypes = [vp]
+        c.tcfd_fft2_last_launch_count.argtypes = [vp]
+        c.tcfd_fft2_irfft2.argtypes = [vp, vp, vp, ci, vp]
+        c.tcfd_fft2_rfft2.argtypes = [vp, vp, vp, ci, vp]
+        c.tcfd_resample_bilinear.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
         sz = ctypes.c_size_t
         c.tcfd_fno_pointwise_linear.argtypes = [vp, vp, vp, vp, ci, ci, ci, sz, vp]
         c.tcfd_fno_layer_glue.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, sz, vp]
@@ -102,6 +114,18 @@ def load_library() -> TcfdLibrary:
     if _LIB is None:
         _LIB = TcfdLibrary(_LIB_PATH)
     return _LIB
+
+
+class HandleStore(dict):
+    """Per-module store of native handles (plans).  Handles wrap ctypes pointers, which can be neither copied
+    nor pickled: ``copy.deepcopy(module)`` / ``torch.save(module)`` see an EMPTY store instead (the copy builds
+    its own handles on first use)."""
+
+    def __deepcopy__(self, memo):
+        return HandleStore()
+
+    def __reduce__(self):
+        return (HandleStore, ())
 
 
 def _darr(vals: Sequence[float]):
@@ -244,6 +268,74 @@ class NS2DPlan:
                        "tcfd_ns2d_residual")
 
 
+class FFT2Plan:
+    """Owns one ``tcfd_fft2_t`` handle (twiddles + scratch) for (n, precision) on the current device: batched
+    rfft2 / irfft2 in the reference's layouts and the bilinear resampling of the data-generation scripts."""
+
+    def __init__(self, lib: TcfdLibrary, n: int, dtype: torch.dtype):
+        assert dtype in (torch.float32, torch.float64)
+        self.lib, self.n, self.nh, self.dtype = lib, n, n // 2 + 1, dtype
+        self.cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
+        self._h = ctypes.c_void_p()
+        rc = lib.c.tcfd_fft2_create(ctypes.byref(self._h), n, 32 if dtype == torch.float32 else 64)
+        if rc != 0:
+            raise ValueError(f"torch-cfd_b200: tcfd_fft2_create failed ({rc}): "
+                             + lib.c.tcfd_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.c.tcfd_fft2_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.c.tcfd_fft2_last_launch_count(self._h))
+
+    def irfft2(self, x_hat: torch.Tensor) -> torch.Tensor:
+        """(*, n, n//2+1) complex -> (*, n, n) real, == torch.fft.irfft2."""
+        if x_hat.dtype != self.cdtype or tuple(x_hat.shape[-2:]) != (self.n, self.nh):
+            raise ValueError(f"irfft2: expected {self.cdtype} (*, {self.n}, {self.nh}), got {x_hat.dtype} {tuple(x_hat.shape)}")
+        xh = x_hat.contiguous()
+        out = torch.empty(tuple(xh.shape[:-1]) + (self.n,), dtype=self.dtype, device=xh.device)
+        count = max(1, xh.numel() // (self.n * self.nh))
+        self.lib.check(self.lib.c.tcfd_fft2_irfft2(self._h, xh.data_ptr(), out.data_ptr(), count, _stream_handle(xh)),
+                       "tcfd_fft2_irfft2")
+        return out
+
+    def rfft2(self, x: torch.Tensor) -> torch.Tensor:
+        """(*, n, n) real -> (*, n, n//2+1) complex, == torch.fft.rfft2."""
+        if x.dtype != self.dtype or tuple(x.shape[-2:]) != (self.n, self.n):
+            raise ValueError(f"rfft2: expected {self.dtype} (*, {self.n}, {self.n}), got {x.dtype} {tuple(x.shape)}")
+        xc = x.contiguous()
+        out = torch.empty(tuple(xc.shape[:-1]) + (self.nh,), dtype=self.cdtype, device=xc.device)
+        count = max(1, xc.numel() // (self.n * self.n))
+        self.lib.check(self.lib.c.tcfd_fft2_rfft2(self._h, xc.data_ptr(), out.data_ptr(), count, _stream_handle(xc)),
+                       "tcfd_fft2_rfft2")
+        return out
+
+
+def resample_bilinear(lib: TcfdLibrary, x: torch.Tensor, n_out: int, dtype: torch.dtype) -> torch.Tensor:
+    """F.interpolate(x.to(dtype), size=(n_out, n_out), mode="bilinear") for square (*, n, n) real fields."""
+    if x.dtype not in (torch.float32, torch.float64) or dtype not in (torch.float32, torch.float64):
+        raise TypeError("resample_bilinear: float32 / float64 only")
+    if x.shape[-1] != x.shape[-2]:
+        raise ValueError("resample_bilinear: square fields only")
+    xc = x.contiguous()
+    n_in = xc.shape[-1]
+    out = torch.empty(tuple(xc.shape[:-2]) + (n_out, n_out), dtype=dtype, device=xc.device)
+    count = max(1, xc.numel() // (n_in * n_in))
+    prec = lambda d: 32 if d == torch.float32 else 64
+    lib.check(lib.c.tcfd_resample_bilinear(xc.data_ptr(), out.data_ptr(), prec(xc.dtype), prec(dtype), count, n_in, n_out,
+                                           _stream_handle(xc)), "tcfd_resample_bilinear")
+    return out
+
+
 _NORMS = {"backward": 0, None: 0, "ortho": 1, "forward": 2}
 
 
@@ -297,6 +389,33 @@ class SConv3dPlan:
                                               None if gx is None else gx.data_ptr(), _ptr_array(gw),
                                               _ptr_array(gbias), float(delta), gy.shape[0], _stream_handle(gy))
         self.lib.check(rc, "tcfd_sconv3d_backward")
+
+    # the two halves as separate calls (tcfd_sconv3d_analysis / synthesis and their adjoints)
+    def yhat_shape(self, batch: int):
+        X, Y, T_in, t_pad, T_out, Ci, Co, mx, my, mt, norm = self.geom
+        return (batch, Co, 2 * mx, 2 * my, mt)
+
+    def analysis(self, x, w, bias, delta, yhat, xhat):
+        rc = self.lib.c.tcfd_sconv3d_analysis(self._h, x.data_ptr(), _ptr_array(w), _ptr_array(bias), float(delta),
+                                              yhat.data_ptr(), None if xhat is None else xhat.data_ptr(),
+                                              x.shape[0], _stream_handle(x))
+        self.lib.check(rc, "tcfd_sconv3d_analysis")
+
+    def synthesis(self, yhat, y):
+        rc = self.lib.c.tcfd_sconv3d_synthesis(self._h, yhat.data_ptr(), y.data_ptr(), yhat.shape[0], _stream_handle(yhat))
+        self.lib.check(rc, "tcfd_sconv3d_synthesis")
+
+    def synthesis_backward(self, gy, gyhat):
+        rc = self.lib.c.tcfd_sconv3d_synthesis_backward(self._h, gy.data_ptr(), gyhat.data_ptr(), gy.shape[0],
+                                                        _stream_handle(gy))
+        self.lib.check(rc, "tcfd_sconv3d_synthesis_backward")
+
+    def analysis_backward(self, gyhat, xhat, w, gx, gw, gbias, delta):
+        rc = self.lib.c.tcfd_sconv3d_analysis_backward(self._h, gyhat.data_ptr(), xhat.data_ptr(), _ptr_array(w),
+                                                       None if gx is None else gx.data_ptr(), _ptr_array(gw),
+                                                       _ptr_array(gbias), float(delta), gyhat.shape[0],
+                                                       _stream_handle(gyhat))
+        self.lib.check(rc, "tcfd_sconv3d_analysis_backward")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -272,18 +272,13 @@ extern "C" size_t tcfd_sconv3d_xhat_elems(const tcfd_sconv3d_t* h, int batch) {
 }
 extern "C" int tcfd_sconv3d_last_launch_count(const tcfd_sconv3d_t* h) { return h ? h->launches : 0; }
 
-extern "C" int tcfd_sconv3d_forward(tcfd_sconv3d_t* h, const void* x, const void* const* w, const void* const* bias,
-                                    float delta, void* y, void* xhat_save, int batch, void* stream_) {
-  if (!h || !x || !w || !y) return sfail(TCFD_ERR_INVALID, "null argument");
-  if (batch < 1 || batch > h->d.max_batch) return sfail(TCFD_ERR_INVALID, "batch outside [1, max_batch]");
-  for (int c = 0; c < 4; ++c)
-    if (!w[c]) return sfail(TCFD_ERR_INVALID, "null weight pointer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+namespace {
+// analysis half: x -> truncated spectrum Xh (kept for backward when xhat_save is given) -> per-mode channel mix -> Yh
+int analysis_impl(tcfd_sconv3d* h, const void* x, const void* const* w, const void* const* bias, float delta, cplx* Yh,
+                  void* xhat_save, int batch, cudaStream_t st) {
   const tcfd_sconv3d_desc_t& d = h->d;
   const int ncol = 2 * d.my * d.mt;
-  h->launches = 0;
   cplx* Xh = xhat_save ? static_cast<cplx*>(xhat_save) : static_cast<cplx*>(h->H1);
-  cplx* Yh = static_cast<cplx*>(h->H2);
   cplx* Z = static_cast<cplx*>(h->Z);
   int rc;
   SconvDims dm = dims_of(h, d.T_in, d.T_out, batch * d.Ci);
@@ -299,35 +294,39 @@ extern "C" int tcfd_sconv3d_forward(tcfd_sconv3d_t* h, const void* x, const void
   }
   a.B = batch; a.Ci = d.Ci; a.Co = d.Co; a.delta = delta;
   TCFD_LAUNCH3(sconv_mix_fwd_kernel, (h->K + 127) / 128, (d.Co + MIX_OT - 1) / MIX_OT, 1, 128, 0, st, Xh, Yh, a, dm);
-  if ((rc = check_launch(h, 0, "mix_fwd"))) return rc;
-  dm = dims_of(h, d.T_in, d.T_out, batch * d.Co);
-  rc = check_launch(h, xaxis(d.X, false, Yh, Z, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Co, st), "xaxis_inv");
-  if (rc) return rc;
-  rc = check_launch(h, planes_inv(d.Y, Z, static_cast<float*>(y), static_cast<const cplx*>(h->S_f),
-                                  static_cast<const cplx*>(h->twy), dm, batch * d.Co * d.X, st), "planes_inv");
-  return rc;
+  return check_launch(h, 0, "mix_fwd");
 }
-
-extern "C" int tcfd_sconv3d_backward(tcfd_sconv3d_t* h, const void* grad_y, const void* xhat, const void* const* w,
-                                     void* grad_x, void* const* grad_w, void* const* grad_bias, float delta, int batch,
-                                     void* stream_) {
-  if (!h || !grad_y || !xhat || !w) return sfail(TCFD_ERR_INVALID, "null argument");
-  if (batch < 1 || batch > h->d.max_batch) return sfail(TCFD_ERR_INVALID, "batch outside [1, max_batch]");
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+// synthesis half: truncated spectrum Yh (batch, Co, 2mx, 2my, mt) -> y
+int synthesis_impl(tcfd_sconv3d* h, const cplx* Yh, void* y, int batch, cudaStream_t st) {
   const tcfd_sconv3d_desc_t& d = h->d;
   const int ncol = 2 * d.my * d.mt;
-  h->launches = 0;
-  cplx* gYh = static_cast<cplx*>(h->H1);
+  cplx* Z = static_cast<cplx*>(h->Z);
+  SconvDims dm = dims_of(h, d.T_in, d.T_out, batch * d.Co);
+  int rc = check_launch(h, xaxis(d.X, false, Yh, Z, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Co, st), "xaxis_inv");
+  if (rc) return rc;
+  return check_launch(h, planes_inv(d.Y, Z, static_cast<float*>(y), static_cast<const cplx*>(h->S_f),
+                                    static_cast<const cplx*>(h->twy), dm, batch * d.Co * d.X, st), "planes_inv");
+}
+// adjoint of the synthesis half: grad_y -> gradient with respect to Yh (torch convention for complex tensors)
+int synthesis_bwd_impl(tcfd_sconv3d* h, const void* grad_y, cplx* gYh, int batch, cudaStream_t st) {
+  const tcfd_sconv3d_desc_t& d = h->d;
+  const int ncol = 2 * d.my * d.mt;
+  cplx* Z = static_cast<cplx*>(h->Z);
+  SconvDims dm = dims_of(h, d.T_out, d.T_in, batch * d.Co);
+  int rc = check_launch(h, planes_fwd(d.Y, static_cast<const float*>(grad_y), Z, static_cast<const cplx*>(h->A_b),
+                                      static_cast<const cplx*>(h->twy), dm, batch * d.Co * d.X, st), "planes_fwd(bwd)");
+  if (rc) return rc;
+  return check_launch(h, xaxis(d.X, true, Z, gYh, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Co, st), "xaxis_fwd(bwd)");
+}
+// adjoint of the analysis half: gYh -> grad_w / grad_bias (needs the saved Xh) and grad_x
+int analysis_bwd_impl(tcfd_sconv3d* h, const cplx* gYh, const void* xhat, const void* const* w, void* grad_x,
+                      void* const* grad_w, void* const* grad_bias, float delta, int batch, cudaStream_t st) {
+  const tcfd_sconv3d_desc_t& d = h->d;
+  const int ncol = 2 * d.my * d.mt;
   cplx* gXh = static_cast<cplx*>(h->H2);
   cplx* Z = static_cast<cplx*>(h->Z);
   int rc;
-  // adjoint of the inverse half: analysis of grad_y with the conjugate-transposed synthesis table
   SconvDims dm = dims_of(h, d.T_out, d.T_in, batch * d.Co);
-  rc = check_launch(h, planes_fwd(d.Y, static_cast<const float*>(grad_y), Z, static_cast<const cplx*>(h->A_b),
-                                  static_cast<const cplx*>(h->twy), dm, batch * d.Co * d.X, st), "planes_fwd(bwd)");
-  if (rc) return rc;
-  rc = check_launch(h, xaxis(d.X, true, Z, gYh, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Co, st), "xaxis_fwd(bwd)");
-  if (rc) return rc;
   MixArgs a{};
   for (int c = 0; c < 4; ++c) {
     if (!w[c]) return sfail(TCFD_ERR_INVALID, "null weight pointer");
@@ -353,4 +352,71 @@ extern "C" int tcfd_sconv3d_backward(tcfd_sconv3d_t* h, const void* grad_y, cons
     if (rc) return rc;
   }
   return TCFD_OK;
+}
+int check_call(const tcfd_sconv3d* h, int batch) {
+  if (!h) return sfail(TCFD_ERR_INVALID, "null argument");
+  if (batch < 1 || batch > h->d.max_batch) return sfail(TCFD_ERR_INVALID, "batch outside [1, max_batch]");
+  return 0;
+}
+}  // namespace
+
+extern "C" size_t tcfd_sconv3d_yhat_elems(const tcfd_sconv3d_t* h, int batch) {
+  return h ? (size_t)batch * h->d.Co * h->K : 0;
+}
+
+extern "C" int tcfd_sconv3d_forward(tcfd_sconv3d_t* h, const void* x, const void* const* w, const void* const* bias,
+                                    float delta, void* y, void* xhat_save, int batch, void* stream_) {
+  if (!h || !x || !w || !y) return sfail(TCFD_ERR_INVALID, "null argument");
+  if (int rc = check_call(h, batch)) return rc;
+  for (int c = 0; c < 4; ++c)
+    if (!w[c]) return sfail(TCFD_ERR_INVALID, "null weight pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  h->launches = 0;
+  cplx* Yh = static_cast<cplx*>(h->H2);
+  if (int rc = analysis_impl(h, x, w, bias, delta, Yh, xhat_save, batch, st)) return rc;
+  return synthesis_impl(h, Yh, y, batch, st);
+}
+
+extern "C" int tcfd_sconv3d_backward(tcfd_sconv3d_t* h, const void* grad_y, const void* xhat, const void* const* w,
+                                     void* grad_x, void* const* grad_w, void* const* grad_bias, float delta, int batch,
+                                     void* stream_) {
+  if (!h || !grad_y || !xhat || !w) return sfail(TCFD_ERR_INVALID, "null argument");
+  if (int rc = check_call(h, batch)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  h->launches = 0;
+  cplx* gYh = static_cast<cplx*>(h->H1);
+  if (int rc = synthesis_bwd_impl(h, grad_y, gYh, batch, st)) return rc;
+  return analysis_bwd_impl(h, gYh, xhat, w, grad_x, grad_w, grad_bias, delta, batch, st);
+}
+
+// ---- the two halves as separate calls (a spectral post-process or a change of mesh sits between them)
+extern "C" int tcfd_sconv3d_analysis(tcfd_sconv3d_t* h, const void* x, const void* const* w, const void* const* bias,
+                                     float delta, void* yhat, void* xhat_save, int batch, void* stream_) {
+  if (!h || !x || !w || !yhat) return sfail(TCFD_ERR_INVALID, "null argument");
+  if (int rc = check_call(h, batch)) return rc;
+  for (int c = 0; c < 4; ++c)
+    if (!w[c]) return sfail(TCFD_ERR_INVALID, "null weight pointer");
+  h->launches = 0;
+  return analysis_impl(h, x, w, bias, delta, static_cast<cplx*>(yhat), xhat_save, batch, static_cast<cudaStream_t>(stream_));
+}
+extern "C" int tcfd_sconv3d_synthesis(tcfd_sconv3d_t* h, const void* yhat, void* y, int batch, void* stream_) {
+  if (!h || !yhat || !y) return sfail(TCFD_ERR_INVALID, "null argument");
+  if (int rc = check_call(h, batch)) return rc;
+  h->launches = 0;
+  return synthesis_impl(h, static_cast<const cplx*>(yhat), y, batch, static_cast<cudaStream_t>(stream_));
+}
+extern "C" int tcfd_sconv3d_synthesis_backward(tcfd_sconv3d_t* h, const void* grad_y, void* grad_yhat, int batch, void* stream_) {
+  if (!h || !grad_y || !grad_yhat) return sfail(TCFD_ERR_INVALID, "null argument");
+  if (int rc = check_call(h, batch)) return rc;
+  h->launches = 0;
+  return synthesis_bwd_impl(h, grad_y, static_cast<cplx*>(grad_yhat), batch, static_cast<cudaStream_t>(stream_));
+}
+extern "C" int tcfd_sconv3d_analysis_backward(tcfd_sconv3d_t* h, const void* grad_yhat, const void* xhat, const void* const* w,
+                                              void* grad_x, void* const* grad_w, void* const* grad_bias, float delta, int batch,
+                                              void* stream_) {
+  if (!h || !grad_yhat || !xhat || !w) return sfail(TCFD_ERR_INVALID, "null argument");
+  if (int rc = check_call(h, batch)) return rc;
+  h->launches = 0;
+  return analysis_bwd_impl(h, static_cast<const cplx*>(grad_yhat), xhat, w, grad_x, grad_w, grad_bias, delta, batch,
+                           static_cast<cudaStream_t>(stream_));
 }

@@ -8,8 +8,10 @@ the reference.  Differences, all deliberate:
 * the equation runs on CUDA tensors only -- there is no CPU fallback; a CPU tensor raises;
 * ``forward`` with an ``RK4CrankNicolsonStepper`` is ONE call into the C ABI for all ``steps``
   (2 kernel launches per RK substage, no torch.fft, no eager elementwise kernels);
-* the forcing must be state independent (both shipped spectral forcings are): its spectrum is
-  evaluated once and added inside the kernel instead of 5x per step (SURVEY.md 8a row A7);
+* a state-independent forcing (both shipped spectral forcings are) is evaluated once and added inside the
+  kernel instead of 5x per step; a user forcing that DOES depend on the state takes
+  the host-driven sub-stage loop: CUDA ``explicit_terms`` (advection) plus the forcing evaluated per
+  sub-stage with the libtcfd transforms (``torch-cfd_b200/fft.py``), as upstream does (equations.py:429-437);
 * the solver is inference-only (``torch.no_grad`` semantics), like every shipped caller.
 """
 from __future__ import annotations
@@ -21,7 +23,7 @@ import torch.nn as nn
 
 from . import _lib
 from .grids import Grid
-from .spectral import brick_wall_filter_2d, spectral_laplacian_2d
+from .spectral import brick_wall_filter_2d, spectral_laplacian_2d, vorticity_to_velocity
 
 Params = Dict[str, torch.Tensor]
 
@@ -103,7 +105,7 @@ class IMEXStepper(nn.Module):
 
     def forward(self, u: torch.Tensor, dt: float, equation: ImplicitExplicitODE,
                 params: Optional[Params] = None) -> torch.Tensor:
-        if isinstance(equation, NavierStokes2DSpectral) and self.fusable(dt, params):
+        if isinstance(equation, NavierStokes2DSpectral) and self.fusable(dt, params) and not equation.state_dependent_forcing:
             return equation._fused_steps(u, dt, 1, self, params, want_dudt=False)[0]
         params = self.params if params is None else params
         alpha, beta = params["alpha"], params["beta"]
@@ -154,7 +156,7 @@ class RK4CrankNicolsonStepper(IMEXStepper):
 
     def forward(self, u: torch.Tensor, dt: float, equation: ImplicitExplicitODE,
                 params: Optional[Params] = None) -> torch.Tensor:
-        if isinstance(equation, NavierStokes2DSpectral):
+        if isinstance(equation, NavierStokes2DSpectral) and not equation.state_dependent_forcing:
             return equation._fused_steps(u, dt, 1, self, params, want_dudt=False)[0]
         params = self.params if params is None else params
         alphas, betas, gammas = params["alphas"], params["betas"], params["gammas"]
@@ -201,7 +203,7 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         self.smooth = smooth
         self.forcing_fn = forcing_fn
         self.solver = solver
-        self._plans = {}
+        self._plans = _lib.HandleStore()
         self._initialize()
 
     def _initialize(self):
@@ -223,11 +225,8 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
             return None
         fn = self.forcing_fn
         vorticity = bool(getattr(fn, "vorticity", False))
-        known = getattr(fn, "state_independent", False) or type(fn).__name__ == "KolmogorovForcing"
-        if not known and not _probe_state_independent(fn, self.grid, vorticity):
-            raise NotImplementedError(
-                "torch-cfd_b200: forcing_fn depends on the state; only state-independent forcings "
-                "(e.g. KolmogorovForcing) can be fused into the CUDA step")
+        if self.state_dependent_forcing:
+            return None  # added per sub-stage by explicit_terms (host-driven loop)
         kx, ky = self.kx.cpu(), self.ky.cpu()
         if vorticity:
             f = fn(self.grid, None)
@@ -237,11 +236,43 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         fy_hat = torch.fft.rfft2(getattr(fy, "data", fy).cpu())
         return 2j * torch.pi * (fy_hat * kx - fx_hat * ky)
 
+    @property
+    def state_dependent_forcing(self) -> bool:
+        """True when ``forcing_fn`` reads its state argument (probed once with two random states; the shipped
+        ``KolmogorovForcing`` and anything that declares ``state_independent = True`` are known not to)."""
+        cached = self.__dict__.get("_sdf")
+        if cached is None:
+            fn = self.forcing_fn
+            if fn is None:
+                cached = False
+            else:
+                known = getattr(fn, "state_independent", False) or type(fn).__name__ == "KolmogorovForcing"
+                cached = not known and not _probe_state_independent(fn, self.grid, bool(getattr(fn, "vorticity", False)))
+            self.__dict__["_sdf"] = cached
+        return cached
+
+    def _dynamic_forcing_hat(self, vort_hat: torch.Tensor) -> torch.Tensor:
+        """Spectrum of a state-dependent forcing for the state ``vort_hat`` (B, n, nh), evaluated like upstream
+        (equations.py:429-437) with the libtcfd transforms: the velocity form receives the physical velocity."""
+        from . import fft as _fft
+        from .spectral import spectral_curl_2d
+        fn = self.forcing_fn
+        kx, ky = self.kx.to(vort_hat.device), self.ky.to(vort_hat.device)
+        data = lambda f: getattr(f, "data", f).to(vort_hat.device)
+        if getattr(fn, "vorticity", False):
+            return _fft.rfft2(data(fn(self.grid, vort_hat)).expand(vort_hat.shape[0], -1, -1).contiguous())
+        (uhat, vhat), _ = vorticity_to_velocity(self.grid, vort_hat, (kx, ky))
+        fx, fy = fn(self.grid, (_fft.irfft2(uhat), _fft.irfft2(vhat)))
+        shape = (vort_hat.shape[0],) + tuple(self.kx.shape[:1]) * 2
+        fx_hat = _fft.rfft2(data(fx).expand(shape).contiguous())
+        fy_hat = _fft.rfft2(data(fy).expand(shape).contiguous())
+        return spectral_curl_2d((fx_hat, fy_hat), (kx, ky))
+
     def invalidate_plan(self):
         """Drop cached device plans (call after editing a buffer or the forcing)."""
         for p in self._plans.values():
             p.close()
-        self._plans = {}
+        self._plans = _lib.HandleStore()
 
     def _plan(self, device: torch.device, batch: int) -> "_lib.NS2DPlan":
         if device.type != "cuda":
@@ -252,9 +283,7 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         plan = self._plans.get(key)
         if plan is not None and plan.max_batch >= batch:
             return plan
-        if plan is not None:
-            plan.close()
-        lib = _lib.load_library()
+        lib = _lib.load_library()  # (a superseded smaller plan is released when its last reference goes)
         kx, ky = self.kx.detach().cpu(), self.ky.detach().cpu()
         dtype = kx.dtype
         n = kx.shape[0]
@@ -288,6 +317,8 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         out = torch.empty_like(w)
         with torch.cuda.device(w.device):
             self._plan(w.device, w.shape[0]).explicit_terms(w, out)
+            if self.state_dependent_forcing:
+                out += self._dynamic_forcing_hat(w)
         return out.reshape(shape)
 
     def implicit_terms(self, vort_hat):
@@ -303,6 +334,8 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         out = torch.empty_like(w)
         with torch.cuda.device(w.device):
             self._plan(w.device, w.shape[0]).residual(w, wt, out)
+            if self.state_dependent_forcing:
+                out -= self._dynamic_forcing_hat(w)
         return out.reshape(shape)
 
     def step(self, *args, **kwargs):
@@ -326,8 +359,8 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
             raise NotImplementedError(
                 "torch-cfd_b200: the CUDA step is inference-only (no autograd through the solver, SURVEY 8b); "
                 "run it under torch.no_grad() or detach the state / freeze the stepper parameters")
-        if isinstance(self.solver, IMEXStepper) and self.solver.fusable(dt):  # includes RK4CrankNicolsonStepper
-            return self._fused_steps(vort_hat, dt, steps, self.solver)
+        if isinstance(self.solver, IMEXStepper) and self.solver.fusable(dt) and not self.state_dependent_forcing:
+            return self._fused_steps(vort_hat, dt, steps, self.solver)  # includes RK4CrankNicolsonStepper
         if self.solver is None:
             raise TypeError("NavierStokes2DSpectral.solver is None: pass solver=RK4CrankNicolsonStepper()")
         vort_old = vort_hat

@@ -16,6 +16,7 @@ from typing import Dict, Optional, Sequence
 
 import torch
 
+from . import fft as _fft
 from .equations import IMEXStepper, NavierStokes2DSpectral
 from .spectral import vorticity_to_velocity
 
@@ -70,7 +71,7 @@ def _trajectory_device(equation, w0, dt, num_steps, record_every_steps, dtype, f
     # every stepper the fused launch serves: RK4CrankNicolsonStepper (an IMEXStepper, as upstream) and the
     # order-1 / 1.5 IMEXStepper with alpha = 0.5; other IMEX settings take the generic loop below
     fused = isinstance(equation, NavierStokes2DSpectral) and isinstance(equation.solver, IMEXStepper) \
-        and equation.solver.fusable(dt) and w0.is_cuda
+        and equation.solver.fusable(dt) and w0.is_cuda and not equation.state_dependent_forcing
     n, nh = w0.shape[-2:]
     w = w0.detach().reshape(-1, n, nh).contiguous()
     B = w.shape[0]
@@ -116,6 +117,32 @@ def _trajectory_device(equation, w0, dt, num_steps, record_every_steps, dtype, f
     return {k: v for k, v in snaps.items() if v is not None}
 
 
+def postprocess_trajectory(result: Dict[str, torch.Tensor], subsample: int = 1, dtype: torch.dtype = torch.float32,
+                           device_result: bool = False) -> Dict[str, torch.Tensor]:
+    """The post-processing loop of the reference's data-generation scripts
+    (fno/data_gen/data_gen_Kolmogorov2d.py:178-188, data_gen_McWilliams2d.py:154-165) ON THE DEVICE:
+
+        value = fft.irfft2(value).real.cpu().to(dtype)
+        if subsample > 1: value = F.interpolate(value, size=(n // subsample,) * 2, mode="bilinear")
+
+    ``result``: dict of (*, n_t, n, n//2+1) complex CUDA tensors (``get_trajectory_imex(..., device_result=True)``).
+    Returns the physical-space fields (*, n_t, ns, ns) of ``dtype`` -- on the host like upstream (the copy moves
+    the subsampled tensors: subsample^2 fewer bytes than the spectra), or on the device with ``device_result``."""
+    out = {}
+    for k, v in result.items():
+        if not torch.is_tensor(v) or not v.is_complex():
+            out[k] = v
+            continue
+        n = v.shape[-2]
+        f = _fft.irfft2(v)
+        if subsample > 1:
+            f = _fft.interpolate_bilinear(f, n // subsample, dtype)
+        elif f.dtype != dtype:
+            f = f.to(dtype)
+        out[k] = f if device_result else _to_host(f)
+    return out
+
+
 def get_trajectory_imex(equation, w0: torch.Tensor, dt: float, num_steps: int = 1, record_every_steps: int = 1,
                         pbar: bool = False, pbar_desc: str = "generating trajectories using RK4",
                         require_grad: bool = False, dtype: torch.dtype = torch.complex64,
@@ -137,23 +164,44 @@ def get_trajectory_imex(equation, w0: torch.Tensor, dt: float, num_steps: int = 
 def get_trajectory_imex_sharded(equation, w0_local: torch.Tensor, dt: float, num_steps: int = 1,
                                 record_every_steps: int = 1, dtype: torch.dtype = torch.complex64,
                                 fields: Sequence[str] = ("vorticity",), group=None,
-                                device_result: bool = False) -> Dict[str, torch.Tensor]:
+                                device_result: bool = False, gather_to="all", physical: bool = False,
+                                subsample: int = 1, out_dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
     """Multi-GPU trajectory: one process per GPU, each stepping ITS contiguous slice ``w0_local`` of
     the global batch (samples never interact: no halo, no data-path collective), followed by the
-    path's only collective -- ``all_gather_into_tensor`` of the recorded fields (NCCL over NVLink on
-    GPUs, gloo in the CPU tests).  Every rank returns the global (B_total, n_t, n, nh) tensors, ranks
-    ordered along the batch axis.  All ranks must hold the same local batch size."""
+    path's only collective on the recorded fields (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+    ``gather_to``: ``"all"`` (default) -- ``all_gather_into_tensor``: every rank returns the global
+    (B_total, n_t, n, nh) tensors, ranks ordered along the batch axis; an ``int`` r -- the fields are gathered on
+    rank r only (the other ranks return an empty dict): one copy of the result crosses NVLink and one rank
+    copies it to its host; ``None`` -- no collective, every rank returns its own shard (what a data-generation
+    job that writes one file per rank wants).  All ranks must hold the same local batch size.
+
+    ``physical=True`` applies ``postprocess_trajectory`` (irfft2 + bilinear subsample + cast, the reference
+    scripts' post-processing loop) on every rank's own shard BEFORE the collective and the device->host copy,
+    which then move ``subsample^2`` fewer bytes."""
     import torch.distributed as dist
     with torch.no_grad():
         snaps = _trajectory_device(equation, w0_local, dt, num_steps, record_every_steps, dtype, tuple(fields), False, "")
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if physical:
+            snaps = postprocess_trajectory(snaps, subsample, out_dtype, device_result=True)
+    single = not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1
+    if single or gather_to is None:
         return {k: (v if device_result else _to_host(v)) for k, v in snaps.items()}
-    world = dist.get_world_size(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     out = {}
     for k, v in snaps.items():
-        real = torch.view_as_real(v.contiguous())
-        gathered = torch.empty((world * real.shape[0],) + tuple(real.shape[1:]), dtype=real.dtype, device=real.device)
-        dist.all_gather_into_tensor(gathered, real, group=group)
-        g = torch.view_as_complex(gathered)
+        real = torch.view_as_real(v.contiguous()) if v.is_complex() else v.contiguous()
+        if gather_to == "all":
+            gathered = torch.empty((world * real.shape[0],) + tuple(real.shape[1:]), dtype=real.dtype, device=real.device)
+            dist.all_gather_into_tensor(gathered, real, group=group)
+        else:
+            dst = int(gather_to)
+            gathered = None
+            if rank == dst:
+                gathered = torch.empty((world * real.shape[0],) + tuple(real.shape[1:]), dtype=real.dtype, device=real.device)
+            dist.gather(real, list(gathered.chunk(world)) if rank == dst else None, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+            if rank != dst:
+                continue
+        g = torch.view_as_complex(gathered) if v.is_complex() else gathered
         out[k] = g if device_result else _to_host(g)
     return out
