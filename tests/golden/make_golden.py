@@ -254,6 +254,40 @@ def sconv_cases(grid32=False):
     np.savez_compressed(os.path.join(HERE, "sconv.npz"), **out)
 
 
+def legacy_case():
+    """legacy_cn.npz: the first-order IMEX / Crank-Nicolson path of fno/data_gen/solvers.py -- one step with a
+    per-sample forcing, update_residual, and a short get_trajectory_imex_crank_nicolson run with subsampling."""
+    torch.set_default_dtype(torch.float32)
+    S = load_solvers()
+    n, bsz, visc, dt, diam = 64, 2, 1e-3, 1e-3, 1.0
+    g = torch.Generator().manual_seed(11)
+    ax = torch.fft.fftfreq(n, d=1.0 / n)
+    kx, ky = torch.meshgrid(ax, ax[: n // 2 + 1], indexing="ij")
+    env = 1.0 / (1 + (torch.sqrt(kx**2 + ky**2) / 4.0) ** 4)
+    w0 = torch.fft.irfft2(torch.fft.rfft2(torch.randn(bsz, n, n, generator=g)) * env, s=(n, n))
+    w0 = 4 * w0 / w0.abs().max()
+    x = torch.linspace(0, 1, n + 1)[:-1]
+    X, Y = torch.meshgrid(x, x, indexing="ij")
+    f = 0.1 * (torch.sin(2 * torch.pi * (X + Y)) + torch.cos(2 * torch.pi * (X + Y)))
+    out = {"w0": _np(w0), "f": _np(f), "visc": visc, "dt": dt, "diam": diam}
+    w_h = fft.rfft2(w0)
+    f_b = torch.stack([f, 0.5 * f.flip(0)])            # per-sample forcing
+    for tag, ff in (("shared", fft.rfft2(f)), ("batched", fft.rfft2(f_b))):
+        w_next, dwdt, _, psi_h, res_h, (kxr, kyr), lap, filt = S.imex_crank_nicolson_step(
+            w_h, ff, visc, dt, diam=diam, dealias=True, output_rfft=True)
+        r2 = S.update_residual(w_next, dwdt, ff if ff.ndim == 3 else ff.unsqueeze(0), visc, (kxr, kyr), lap,
+                               dealias_filter=filt, dealias=True)
+        for k, v in (("w_next", w_next), ("dwdt", dwdt), ("psi", psi_h), ("res", res_h), ("res_next", r2)):
+            out[f"step_{tag}_{k}"] = _np(v)
+    out["f_b"] = _np(f_b)
+    res = S.get_trajectory_imex_crank_nicolson(w0, f, visc=visc, T=0.02, delta_t=dt, record_steps=4, diam=diam,
+                                               dealias=True, subsample=2, pbar=False)
+    for k, v in res.items():
+        out[f"traj_{k}"] = _np(v)
+    print("legacy", {k: tuple(v.shape) for k, v in res.items()})
+    np.savez_compressed(os.path.join(HERE, "legacy_cn.npz"), **out)
+
+
 def sfno_case():
     """sfno.npz: the x / y change of mesh of SpectralConv.forward (fno/base.py:229-237), SpectralConvT with the
     HelmholtzProjection post-process (fno/sfno.py:116-193, :452) -- values and all gradients -- and a small SFNO
@@ -306,6 +340,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sfno":
         sfno_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "legacy":
+        legacy_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "signatures":
         signature_case()
         sys.exit(0)
@@ -332,3 +369,4 @@ if __name__ == "__main__":
     sconv_cases()
     sconv_cases(grid32=True)
     sfno_case()
+    legacy_case()

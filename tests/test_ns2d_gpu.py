@@ -472,3 +472,38 @@ def test_state_dependent_forcing_host_loop():
                 u = O.implicit_solve(tb, u + g[k] * 1e-3 * h + mu * O.implicit_terms(tb, u), mu)
         assert rel_l2(w, u) < 1e-11
         assert rel_l2(dwdt, (u - w0) / 3e-3) < 1e-7
+
+
+def test_legacy_imex_crank_nicolson_vs_reference_golden():
+    """fno/data_gen/solvers.py:49-188, :268-448 (fixture generated from the reference itself):
+    one step with a batch-shared forcing (ONE fused launch) and with a per-sample forcing (CUDA explicit terms +
+    the reference's update formula), update_residual, and the trajectory driver with bilinear subsampling."""
+    import torch_cfd_b200 as T
+    g = load_golden("legacy_cn")
+    visc, dt, diam = float(g["visc"]), float(g["dt"]), float(g["diam"])
+    w0, f, f_b = (torch.from_numpy(g[k]).to(DEV) for k in ("w0", "f", "f_b"))
+    with default_dtype(torch.float32):
+        w_h = T.fft.rfft2(w0)
+        for tag, ff in (("shared", T.fft.rfft2(f)), ("batched", T.fft.rfft2(f_b))):
+            w_next, dwdt, w_in, psi_h, res_h, mesh, lap, filt = T.imex_crank_nicolson_step(
+                w_h, ff, visc, dt, diam=diam, dealias=True, output_rfft=True)
+            assert torch.equal(w_in, w_h)
+            assert rel_l2(w_next, torch.from_numpy(g[f"step_{tag}_w_next"])) < 2e-6
+            scale = float(np.linalg.norm(g[f"step_{tag}_dwdt"]))
+            assert float(torch.linalg.norm(dwdt.cpu() - torch.from_numpy(g[f"step_{tag}_dwdt"]))) / scale < 2e-4
+            assert rel_l2(psi_h, torch.from_numpy(g[f"step_{tag}_psi"])) < 2e-6
+            # the residual is a difference of O(|dw/dt|) terms: compare on that scale
+            assert float(torch.linalg.norm(res_h.cpu() - torch.from_numpy(g[f"step_{tag}_res"]))) / scale < 2e-4
+            r2 = T.update_residual(torch.from_numpy(g[f"step_{tag}_w_next"]).to(DEV), torch.from_numpy(g[f"step_{tag}_dwdt"]).to(DEV),
+                                   ff if ff.ndim == 3 else ff.unsqueeze(0), visc, mesh, lap, dealias_filter=filt, dealias=True)
+            assert float(torch.linalg.norm(r2.cpu() - torch.from_numpy(g[f"step_{tag}_res_next"]))) / scale < 2e-5
+        res = T.get_trajectory_imex_crank_nicolson(w0, f, visc=visc, T=0.02, delta_t=dt, record_steps=4, diam=diam,
+                                                   dealias=True, subsample=2, pbar=False)
+        for k in ("vorticity", "vorticity_t", "stream", "residual", "t_steps"):
+            ref = torch.from_numpy(g[f"traj_{k}"])
+            assert res[k].shape == ref.shape and res[k].dtype == ref.dtype and not res[k].is_cuda
+            if k == "residual":
+                err = float(torch.linalg.norm(res[k] - ref)) / float(np.linalg.norm(g["traj_vorticity_t"]))
+            else:
+                err = rel_l2(res[k], ref)
+            assert err < (2e-4 if k in ("vorticity_t", "residual") else 1e-5), (k, err)

@@ -7,6 +7,7 @@ from .spectral import (brick_wall_filter_2d, fft_mesh_2d, spectral_curl_2d, spec
                        spectral_grad_2d, spectral_laplacian_2d, spectral_rot_2d, vorticity_to_velocity)
 from .equations import (IMEXStepper, ImplicitExplicitODE, NavierStokes2DSpectral,  # noqa: F401
                         RK4CrankNicolsonStepper, stable_time_step)
-from .solvers import get_trajectory_imex, get_trajectory_imex_sharded, postprocess_trajectory  # noqa: F401
+from .solvers import (get_trajectory_imex, get_trajectory_imex_crank_nicolson, get_trajectory_imex_sharded,  # noqa: F401
+                      imex_crank_nicolson_step, postprocess_trajectory, update_residual)
 from . import fft  # noqa: F401
 from . import fno  # noqa: F401
