@@ -201,6 +201,9 @@ int tcfd_fno_pointwise_linear(const float* x, float* y, const float* w, const fl
 int tcfd_fno_layer_glue(const float* conv_out, const float* x, float* y, const float* w1, const float* b1,
                         const float* w2, const float* b2, const float* ww, const float* bw, int act, int batch, int C,
                         size_t npts, void* stream);
+/* which kernel the last tcfd_fno_layer_glue call of this process launched: 1 = tensor cores (tcgen05 3xTF32 products,
+ * accumulators in TMEM: even C <= 32 on a CUDA device), 0 = CUDA cores (odd C, TCFD_GLUE_TC=0, host-emulation build) */
+int tcfd_fno_layer_glue_path(void);
 int tcfd_fno_project(const float* x, float* y, const float* w1, const float* b1, const float* w2, const float* b2,
                      int act, int batch, int C, int M, size_t npts, void* stream);
 

@@ -170,3 +170,30 @@ def test_fno3d_fused_inference_matches_torch_op_path(width, last_act, padding):
     y_ops = y_ops.detach()
     err = (torch.linalg.norm(y_fused - y_ops) / torch.linalg.norm(y_ops)).item()
     assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("C,shape,act", [(20, (2, 16, 16, 10), True), (10, (3, 7, 9, 11), False), (32, (2, 16, 16, 10), True),
+                                         (2, (1, 4, 8, 8), True), (14, (2, 8, 8, 9), False), (24, (1, 8, 16, 3), True),
+                                         (7, (1, 5, 5, 5), True)])
+def test_layer_glue_tensor_core_path_vs_reference_ops(C, shape, act, monkeypatch):
+    """tcfd_fno_layer_glue (fno/fno3d.py:223-230): the tcgen05 path (3xTF32 products, accumulators in TMEM; even C)
+    and the CUDA-core path against the reference's torch ops in exact fp32; full and ragged 128-point tiles."""
+    import ctypes
+    import torch.nn as nn
+    from torch_cfd_b200 import _lib
+    lib = _lib.load_library()
+    torch.manual_seed(1)
+    mlp1, mlp2, w = nn.Conv3d(C, C, 1), nn.Conv3d(C, C, 1), nn.Conv3d(C, C, 1)
+    c, x = torch.randn(shape[0], C, *shape[1:]), torch.randn(shape[0], C, *shape[1:])
+    with torch.no_grad():
+        ref = mlp2(nn.functional.gelu(mlp1(c))) + w(x)
+        ref = nn.functional.gelu(ref) if act else ref
+    hw = _lib.fno_glue_host_weights(mlp1.weight, mlp1.bias, mlp2.weight, mlp2.bias, w.weight, w.bias)
+    lib.c.tcfd_fno_layer_glue_path.restype = ctypes.c_int
+    y = _lib.fno_layer_glue(lib, c.to(DEV), x.to(DEV), hw, act)
+    assert lib.c.tcfd_fno_layer_glue_path() == (1 if C % 2 == 0 else 0)
+    assert rel_l2(y, ref) < 3e-6           # (1e-5 is the bar of SURVEY 8d)
+    monkeypatch.setenv("TCFD_GLUE_TC", "0")
+    y0 = _lib.fno_layer_glue(lib, c.to(DEV), x.to(DEV), hw, act)
+    assert lib.c.tcfd_fno_layer_glue_path() == 0
+    assert rel_l2(y0, ref) < 1e-6

@@ -19,6 +19,10 @@
 
 #include "../../include/tcfd.h"
 #include "tcfd_common.cuh"
+#ifndef TCFD_EMU
+#include <cstring>
+#include "fno_glue_tc.cuh"
+#endif
 
 extern "C" void tcfd_set_last_error(const char* msg);
 
@@ -378,6 +382,9 @@ GlueWeights<CP> pack_glue(const float* w1, const float* b1, const float* w2, con
   return W;
 }
 
+namespace { int g_last_glue_path = 0; }
+extern "C" int tcfd_fno_layer_glue_path(void) { return g_last_glue_path; }
+
 extern "C" int tcfd_fno_layer_glue(const float* conv_out, const float* x, float* y, const float* w1, const float* b1,
                                    const float* w2, const float* b2, const float* ww, const float* bw, int act, int batch,
                                    int C, size_t npts, void* stream_) {
@@ -385,6 +392,54 @@ extern "C" int tcfd_fno_layer_glue(const float* conv_out, const float* x, float*
   if (batch < 1 || C < 1 || npts < 1) return fail(TCFD_ERR_INVALID, "bad sizes");
   if (C > 32) return fail(TCFD_ERR_INVALID, "layer glue: at most 32 channels");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
+#ifndef TCFD_EMU
+  {
+    // tensor-core path (fno_glue_tc.cuh): the three C x C products as 3xTF32 UMMAs with the accumulators in TMEM.
+    // TCFD_GLUE_TC=0 selects the CUDA-core kernel below (cross-check / A-B timing); TCFD_GLUE_SWAP is a bring-up knob.
+    const char* e = getenv("TCFD_GLUE_TC");
+    const bool use_tc = !(e && atoi(e) == 0);
+    const char* sw = getenv("TCFD_GLUE_SWAP");
+    const bool swap = sw && atoi(sw) != 0;
+    if (use_tc && C % 2 == 0 && npts < ((size_t)1 << 27)) {
+      static int sms = 0;
+      if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      }
+      const size_t tps = (npts + 127) / 128, ntiles = tps * batch;
+      const bool tail = npts % 128 != 0;
+      // dynamic shared memory only pads the footprint so that the resident CTAs of an SM never ask for more than
+      // the 512 TMEM columns: 4 CTAs (128 columns each) for C <= 24, 2 CTAs (256 columns) above
+      const int per_sm = C <= 24 ? 4 : 2;
+      const size_t pad = C <= 24 ? 30 * 1024 : 64 * 1024;
+      const size_t grid = ntiles < (size_t)sms * per_sm ? ntiles : (size_t)sms * per_sm;
+#define TCFD_GLUE_TC_RUN(cc, tl, sw_)                                                                                  \
+  {                                                                                                                    \
+    auto k = gluetc::fno_layer_glue_tc_kernel<cc, tl, sw_>;                                                            \
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad) != cudaSuccess)                 \
+      return fail(TCFD_ERR_CUDA, "cudaFuncSetAttribute failed");                                                       \
+    const auto W = gluetc::pack_tc<(cc + 7) / 8 * 8>(w1, b1, w2, b2, ww, bw, C);                                       \
+    g_last_glue_path = 1;                                                                                              \
+    k<<<(unsigned)grid, 256, pad, st>>>(conv_out, x, y, W, act, npts, tps, ntiles);                                    \
+    return after_launch("fno_layer_glue_tc_kernel");                                                                   \
+  }
+#define TCFD_GLUE_TC_CASE(cc)                                  \
+  if (C == cc && !swap) {                                      \
+    if (tail) TCFD_GLUE_TC_RUN(cc, true, false)                \
+    else TCFD_GLUE_TC_RUN(cc, false, false)                    \
+  }
+      TCFD_GLUE_TC_CASE(2) TCFD_GLUE_TC_CASE(4) TCFD_GLUE_TC_CASE(6) TCFD_GLUE_TC_CASE(8) TCFD_GLUE_TC_CASE(10)
+      TCFD_GLUE_TC_CASE(12) TCFD_GLUE_TC_CASE(14) TCFD_GLUE_TC_CASE(16) TCFD_GLUE_TC_CASE(18) TCFD_GLUE_TC_CASE(20)
+      TCFD_GLUE_TC_CASE(22) TCFD_GLUE_TC_CASE(24) TCFD_GLUE_TC_CASE(26) TCFD_GLUE_TC_CASE(28) TCFD_GLUE_TC_CASE(30)
+      TCFD_GLUE_TC_CASE(32)
+      if (C == 20 && swap) TCFD_GLUE_TC_RUN(20, true, true)
+#undef TCFD_GLUE_TC_CASE
+#undef TCFD_GLUE_TC_RUN
+    }
+  }
+#endif
+  g_last_glue_path = 0;
   const int CP = (C + 3) / 4 * 4;
   int P = points_per_thread(npts, conv_out, x, y);
   // (a 4-point streaming variant -- each weight serving 4 multiply-adds -- was measured slower: 5.6 vs 3.6 ms)
