@@ -254,6 +254,19 @@ def sconv_cases(grid32=False):
     np.savez_compressed(os.path.join(HERE, "sconv.npz"), **out)
 
 
+def ic_case():
+    """ic.npz: McWilliams vorticity fields of the reference generator (torch_cfd/initial_conditions.py:170-199)."""
+    torch.set_default_dtype(torch.float32)
+    from torch_cfd.grids import Grid
+    from torch_cfd.initial_conditions import vorticity_field
+    out = {}
+    for n, pk, seed in ((64, 4, 0), (128, 6, 3)):
+        grid = Grid(shape=(n, n), domain=((0, 2 * torch.pi), (0, 2 * torch.pi)))
+        out[f"w_{n}_{pk}_{seed}"] = _np(vorticity_field(grid, pk, random_state=seed).data)
+    np.savez_compressed(os.path.join(HERE, "ic.npz"), **out)
+    print("ic", {k: v.shape for k, v in out.items()})
+
+
 def legacy_case():
     """legacy_cn.npz: the first-order IMEX / Crank-Nicolson path of fno/data_gen/solvers.py -- one step with a
     per-sample forcing, update_residual, and a short get_trajectory_imex_crank_nicolson run with subsampling."""
@@ -340,6 +353,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sfno":
         sfno_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ic":
+        ic_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "legacy":
         legacy_case()
         sys.exit(0)
@@ -370,3 +386,4 @@ if __name__ == "__main__":
     sconv_cases(grid32=True)
     sfno_case()
     legacy_case()
+    ic_case()

@@ -507,3 +507,29 @@ def test_legacy_imex_crank_nicolson_vs_reference_golden():
             else:
                 err = rel_l2(res[k], ref)
             assert err < (2e-4 if k in ("vorticity_t", "residual") else 1e-5), (k, err)
+
+
+def test_initial_condition_generators():
+    """McWilliams vorticity field against the reference generator's output (fixture ic.npz,
+    torch_cfd/initial_conditions.py:170-199); GRF2d.sample and the spectral Poisson apply against torch.fft."""
+    import torch_cfd_b200 as T
+    from torch_cfd_b200.initial_conditions import spectral_poisson_apply
+    g = load_golden("ic")
+    with default_dtype(torch.float32):
+        for n, pk, seed in ((64, 4, 0), (128, 6, 3)):
+            grid = T.Grid(shape=(n, n), domain=((0, 2 * torch.pi), (0, 2 * torch.pi)))
+            ref = torch.from_numpy(g[f"w_{n}_{pk}_{seed}"])
+            w = T.vorticity_field(grid, pk, random_state=seed, device=DEV)
+            assert w.data.is_cuda and rel_l2(w.data, ref) < 1e-5
+            wh = T.vorticity_field(grid, pk, random_state=seed, device=DEV, spectrum=True)
+            assert rel_l2(wh, torch.fft.rfft2(ref)) < 1e-5
+        grf = T.GRF2d(n=64, alpha=2.5, tau=7, device=DEV)
+        s = grf.sample(3, random_state=5)
+        torch.cuda.manual_seed(5)
+        torch.random.manual_seed(5)
+        coeff = torch.randn(3, 2, 64, 64, device=DEV)
+        sr = torch.fft.ifftn(grf.sqrt_eig.cpu() * (coeff[:, 0] + 1j * coeff[:, 1]).cpu(), dim=(-1, -2)).real
+        assert rel_l2(s, sr) < 1e-5
+        x = torch.randn(2, 64, 64)
+        mult = torch.rand(64, 33)
+        assert rel_l2(spectral_poisson_apply(x.to(DEV), mult), torch.fft.irfft2(mult * torch.fft.rfft2(x))) < 2e-6

@@ -11,3 +11,5 @@ from .solvers import (get_trajectory_imex, get_trajectory_imex_crank_nicolson, g
                       imex_crank_nicolson_step, postprocess_trajectory, update_residual)
 from . import fft  # noqa: F401
 from . import fno  # noqa: F401
+from . import initial_conditions  # noqa: F401
+from .initial_conditions import GRF2d, vorticity_field  # noqa: F401

@@ -293,7 +293,13 @@ int analysis_impl(tcfd_sconv3d* h, const void* x, const void* const* w, const vo
     a.bias[c] = bias ? static_cast<const cplx*>(bias[c]) : nullptr;
   }
   a.B = batch; a.Ci = d.Ci; a.Co = d.Co; a.delta = delta;
-  TCFD_LAUNCH3(sconv_mix_fwd_kernel, (h->K + 127) / 128, (d.Co + MIX_OT - 1) / MIX_OT, 1, 128, 0, st, Xh, Yh, a, dm);
+  {
+    // enough CTAs for every SM: split the batch tiles over grid.z when modes x channel tiles alone are few
+    const int gx = (h->K + 127) / 128, gy = (d.Co + MIX_OT - 1) / MIX_OT, bt = (batch + MIX_BT - 1) / MIX_BT;
+    int gz = 1184 / (gx * gy);
+    gz = gz < 1 ? 1 : (gz > bt ? bt : gz);
+    TCFD_LAUNCH3(sconv_mix_fwd_kernel, gx, gy, gz, 128, 0, st, Xh, Yh, a, dm);
+  }
   return check_launch(h, 0, "mix_fwd");
 }
 // synthesis half: truncated spectrum Yh (batch, Co, 2mx, 2my, mt) -> y
@@ -342,7 +348,10 @@ int analysis_bwd_impl(tcfd_sconv3d* h, const cplx* gYh, const void* xhat, const 
     if ((rc = check_launch(h, 0, "mix_bwd_w"))) return rc;
   }
   if (grad_x) {
-    TCFD_LAUNCH3(sconv_mix_bwd_x_kernel, (h->K + 127) / 128, (d.Ci + MIX_OT - 1) / MIX_OT, 1, 128, 0, st, gYh, gXh, a, dm);
+    const int gx = (h->K + 127) / 128, gy = (d.Ci + MIX_OT - 1) / MIX_OT, bt = (batch + MIX_BT - 1) / MIX_BT;
+    int gz = 1184 / (gx * gy);
+    gz = gz < 1 ? 1 : (gz > bt ? bt : gz);
+    TCFD_LAUNCH3(sconv_mix_bwd_x_kernel, gx, gy, gz, 128, 0, st, gYh, gXh, a, dm);
     if ((rc = check_launch(h, 0, "mix_bwd_x"))) return rc;
     dm = dims_of(h, d.T_out, d.T_in, batch * d.Ci);
     rc = check_launch(h, xaxis(d.X, false, gXh, Z, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Ci, st), "xaxis_inv(bwd)");

@@ -610,7 +610,8 @@ sconv_mix_fwd_kernel(const cx<float>* __restrict__ Xh, cx<float>* __restrict__ Y
     const cx<float> bb = a.bias[corner][widx];
     bias = cx<float>{a.delta * bb.x, a.delta * bb.y};
   }
-  for (int b0 = 0; b0 < a.B; b0 += MIX_BT) {
+  // batch tiles are spread over blockIdx.z (few modes x many samples would otherwise leave most SMs idle)
+  for (int b0 = (int)blockIdx.z * MIX_BT; b0 < a.B; b0 += (int)gridDim.z * MIX_BT) {
     cx<float> acc[MIX_BT][MIX_OT];
 #pragma unroll
     for (int j = 0; j < MIX_BT; ++j)
@@ -646,7 +647,7 @@ sconv_mix_bwd_x_kernel(const cx<float>* __restrict__ gYh, cx<float>* __restrict_
   int corner, widx;
   mode_split(k, d, corner, widx);
   const cx<float>* w = a.w[corner] + widx;
-  for (int b0 = 0; b0 < a.B; b0 += MIX_BT) {
+  for (int b0 = (int)blockIdx.z * MIX_BT; b0 < a.B; b0 += (int)gridDim.z * MIX_BT) {
     cx<float> acc[MIX_BT][MIX_OT];
 #pragma unroll
     for (int j = 0; j < MIX_BT; ++j)
