@@ -70,8 +70,9 @@ size_t tcfd_ns2d_workspace_bytes(const tcfd_ns2d_t* h);
  * failure through the handle's host-visible error word; meaningful after the stream was synchronised.
  * Every tcfd_ns2d_step call performs this check on entry. */
 int tcfd_ns2d_check(const tcfd_ns2d_t* h);
-/* launch schedule of tcfd_ns2d_step on this handle: 1 = one persistent dataflow launch per call
- * (n >= 256; environment TCFD_FLOW=0 at creation selects the other), 0 = two launches per substage */
+/* launch schedule of tcfd_ns2d_step on this handle: 1 = ONE launch per call -- the persistent dataflow kernel
+ * (n >= 256; environment TCFD_FLOW=0 at creation selects the other) or the shared-memory-resident kernel
+ * (n <= 64; TCFD_SMALL=0 selects the other) --, 0 = two launches per substage */
 int tcfd_ns2d_schedule(const tcfd_ns2d_t* h);
 /* number of kernel launches the last tcfd_ns2d_* compute call enqueued */
 int tcfd_ns2d_last_launch_count(const tcfd_ns2d_t* h);

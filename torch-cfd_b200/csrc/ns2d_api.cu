@@ -61,6 +61,8 @@ struct tcfd_ns2d {
   cudaEvent_t ev_start = nullptr, ev_end = nullptr;
   size_t ws_bytes = 0;
   int launches = 0;
+  // whole-call resident kernel for n <= 64 (ns2d_small.cuh)
+  bool small = false;
   // third-generation persistent dataflow schedule (ns2d_flow.cuh)
   bool flow = false;
   int* sync_dev = nullptr;   // ticket + per-sample counters
@@ -369,6 +371,49 @@ int flow_step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int 
   return 0;
 }
 
+// Small grids (n <= 64): the whole call as ONE launch, one CTA per sample, state resident in shared memory
+// (ns2d_small.cuh).  TCFD_SMALL=0 selects the two-launches-per-sub-stage kernels instead (cross-check).
+template <class T>
+int small_step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int batch, int steps, int nstages,
+                    const double* beta, const double* gdt, const double* mu, double inv_total_dt, void* stream) {
+  typedef tcfd::cx<T> C;
+  tcfd::FlowParams<T> fp;
+  std::memset(&fp, 0, sizeof(fp));
+  fill_params<T>(h, fp.p, batch);
+  fp.p.mode = tcfd::UPD_RK;
+  fp.p.w_in = static_cast<const C*>(w_in);
+  fp.p.w_out = static_cast<C*>(w_out);
+  if (dwdt) {
+    fp.p.dwdt = static_cast<C*>(dwdt);
+    fp.p.inv_tdt = (T)inv_total_dt;
+  }
+  fp.nsub = steps * nstages;
+  fp.nstages = nstages;
+  for (int k = 0; k < nstages; ++k) {
+    fp.beta[k] = (T)beta[k];
+    fp.gdt[k] = (T)gdt[k];
+    fp.mu[k] = (T)mu[k];
+    fp.rd_h[k] = (k > 0 && beta[k] != 0.0) ? 1 : 0;
+    fp.wr_h[k] = (k + 1 < nstages && beta[k + 1] != 0.0) ? 1 : 0;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timed) {
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, static_cast<cudaStream_t>(stream)));
+  }
+  const int rc = h->entry.launch_small(&fp, batch, stream);
+  if (h->timed) {
+    CUDA_TRY(cudaEventRecord(e1, static_cast<cudaStream_t>(stream)));
+    h->ev.push_back(e0);
+    h->ev.push_back(e1);
+    h->ev_kind.push_back(TCFD_K_ROWS_FULL);
+  }
+  h->launches++;
+  if (rc != 0) return fail(TCFD_ERR_CUDA, std::string("resident small-grid kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+  return 0;
+}
+
 template <class T>
 int eval_impl(tcfd_ns2d* h, int mode, const void* w_in, const void* wt_in, void* out, int batch, void* stream) {
   typedef tcfd::cx<T> C;
@@ -450,6 +495,8 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
     // 10-40 %; default W = 64.
     h->flow = h->entry.launch_flow != nullptr;
     if (const char* e = getenv("TCFD_FLOW")) h->flow = h->flow && atoi(e) != 0;
+    h->small = h->entry.launch_small != nullptr;
+    if (const char* e = getenv("TCFD_SMALL")) h->small = h->small && atoi(e) != 0;
     if (h->flow) {
       int W = 64;
       if (const char* e = getenv("TCFD_FLOW_W")) W = atoi(e) > 0 ? atoi(e) : W;
@@ -612,7 +659,7 @@ extern "C" int tcfd_ns2d_flow_profile(tcfd_ns2d_t* h, unsigned long long* out16)
   return TCFD_OK;
 }
 
-extern "C" int tcfd_ns2d_schedule(const tcfd_ns2d_t* h) { return (h && h->flow) ? 1 : 0; }
+extern "C" int tcfd_ns2d_schedule(const tcfd_ns2d_t* h) { return (h && (h->flow || h->small)) ? 1 : 0; }
 
 extern "C" size_t tcfd_ns2d_workspace_bytes(const tcfd_ns2d_t* h) { return h ? h->ws_bytes : 0; }
 extern "C" int tcfd_ns2d_last_launch_count(const tcfd_ns2d_t* h) { return h ? h->launches : 0; }
@@ -627,6 +674,10 @@ extern "C" int tcfd_ns2d_step(tcfd_ns2d_t* h, const void* w_in, void* w_out, voi
   if (steps < 1 || nstages < 1) return fail(TCFD_ERR_INVALID, "steps and nstages must be >= 1");
   h->launches = 0;
   if ((rc = tcfd_ns2d_check(h))) return rc;
+  if (h->small && nstages <= tcfd::FLOW_MAX_STAGES)
+    return h->prec == 32
+               ? small_step_impl<float>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream)
+               : small_step_impl<double>(h, w_in, w_out, dwdt, batch, steps, nstages, beta, gdt, mu, inv_total_dt, stream);
   if (h->flow && nstages <= tcfd::FLOW_MAX_STAGES) {
     const int nd = h->n / 4 + 1, nq = h->n / 4;
     const double items = (double)batch * ((double)nd + (double)steps * nstages * (nd + nq));

@@ -2,6 +2,7 @@
 // Exports a C launcher table entry used by ns2d_api.cu.  N >= 256 gets the second-generation
 // kernels (ns2d_v2.cuh), smaller grids the CTA-tiled ones (ns2d_kernels.cuh).
 #include "ns2d_flow.cuh"
+#include "ns2d_small.cuh"
 #include "ns2d_plan.h"
 #include <cstdio>
 #include <cstdlib>
@@ -300,6 +301,38 @@ int launch(int which, const void* params, const void* maps, int num_sms, void* s
 #endif
 }
 
+#if TCFD_N <= 64
+// groups per CTA of the resident kernel: as many as 1024 threads / the 227 KB of shared memory allow
+constexpr int SMALL_G_THREADS = 512 / NT;
+constexpr int small_groups() {
+  int g = SMALL_G_THREADS;
+  while (g > 1 && SmallSmem<real_t, N, 1>::OFF_BUF + (size_t)g * N * sizeof(cx<real_t>) > 232448 - 1024) --g;
+  return g;
+}
+int launch_small(const void* params, int batch, void* stream_) {
+  constexpr int G = small_groups();
+  static int ready[MAX_DEV];
+  auto k = ns2d_small_kernel<real_t, N, G>;
+  constexpr size_t smem = SmallSmem<real_t, N, G>::BYTES;
+#ifndef TCFD_EMU
+  int& r = ready[cur_dev()];
+  if (!r) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    r = 1;
+  }
+#else
+  (void)ready;
+#endif
+  TCFD_LAUNCH(k, batch, G * NT, smem, static_cast<cudaStream_t>(stream_), *static_cast<const FlowParams<real_t>*>(params));
+#ifndef TCFD_EMU
+  return (int)cudaGetLastError();
+#else
+  return 0;
+#endif
+}
+#endif
+
 #if TCFD_N >= 256
 int launch_flow(const void* params, const void* maps, int num_sms, void* stream_, const tcfd_flow_window_t* win) {
   int rc = v2::launch_flow(*static_cast<const FlowParams<real_t>*>(params), static_cast<const TileMaps*>(maps), num_sms,
@@ -332,5 +365,10 @@ extern "C" void TCFD_ENTRY(TCFD_PREC, TCFD_N)(tcfd_ns2d_entry_t* e) {
 #else
   e->flow_ctas_per_sm = 0;
   e->launch_flow = nullptr;
+#endif
+#if TCFD_N <= 64
+  e->launch_small = &launch_small;
+#else
+  e->launch_small = nullptr;
 #endif
 }

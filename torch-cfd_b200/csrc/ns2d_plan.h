@@ -19,4 +19,7 @@ typedef struct {
   // null when the size has no such kernel
   int (*launch_flow)(const void* flow_params, const void* maps, int num_sms, void* stream, const tcfd_flow_window_t* win);
   int flow_ctas_per_sm;  // CTAs per SM the flow kernel's shared memory allows (0: does not fit)
+  // whole-call resident kernel for small grids (ns2d_small.cuh, n <= 64): params = const tcfd::FlowParams<T>*, one CTA
+  // per sample; null when the size has no such kernel
+  int (*launch_small)(const void* flow_params, int batch, void* stream);
 } tcfd_ns2d_entry_t;
