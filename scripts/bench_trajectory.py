@@ -16,6 +16,9 @@ ap.add_argument("--n", type=int, default=512)
 ap.add_argument("--steps", type=int, default=2000)
 ap.add_argument("--every", type=int, default=20)
 ap.add_argument("--fields", default="vorticity", help="comma list of vorticity,stream,vort_t,residual")
+ap.add_argument("--gather-to", default="none", help="all | none | <rank>: collection of the recorded fields (get_trajectory_imex_sharded)")
+ap.add_argument("--physical", type=int, default=1, help="1: irfft2 (+ bilinear subsample) on the device before the copy (data-gen post-processing)")
+ap.add_argument("--subsample", type=int, default=1)
 a = ap.parse_args()
 world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
@@ -34,19 +37,29 @@ ns = T.NavierStokes2DSpectral(viscosity=VISC, grid=grid, drag=DRAG, smooth=True,
                               solver=T.RK4CrankNicolsonStepper())
 w0 = make_state(n, B, torch.float32, rank * B).to(dev)
 fields = tuple(a.fields.split(","))
-T.get_trajectory_imex_sharded(ns, w0, DT, num_steps=2 * a.every, record_every_steps=a.every, fields=fields, device_result=True)
+gather_to = None if a.gather_to == "none" else ("all" if a.gather_to == "all" else int(a.gather_to))
+kw = dict(record_every_steps=a.every, fields=fields, gather_to=gather_to, physical=bool(a.physical), subsample=a.subsample)
+T.get_trajectory_imex_sharded(ns, w0, DT, num_steps=2 * a.every, device_result=True, **kw)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
+# (1) device part only: steps + recording (+ post-processing + collective), results left on the device
 t0 = time.perf_counter()
-out = T.get_trajectory_imex_sharded(ns, w0, DT, num_steps=a.steps, record_every_steps=a.every, fields=fields, device_result=True)
+out = T.get_trajectory_imex_sharded(ns, w0, DT, num_steps=a.steps, device_result=True, **kw)
 torch.cuda.synchronize()
 t_dev = time.perf_counter() - t0
-from torch_cfd_b200.solvers import _to_host  # what get_trajectory_imex(..., device_result=False) does
-host = {k: _to_host(v) for k, v in out.items()}
+shape = tuple(next(iter(out.values())).shape) if out else ()
+finite = bool(torch.isfinite(next(iter(out.values()))[:, -1].float() if out and not next(iter(out.values())).is_complex()
+                             else torch.view_as_real(next(iter(out.values()))[:, -1])).all().item()) if out else True
+del out
+if world > 1:
+    dist.barrier()
+# (2) end to end: the same call returning HOST tensors, as the data-generation scripts consume them
+t0 = time.perf_counter()
+host = T.get_trajectory_imex_sharded(ns, w0, DT, num_steps=a.steps, device_result=False, **kw)
+torch.cuda.synchronize()
 t_all = time.perf_counter() - t0
-shape = tuple(next(iter(out.values())).shape)
-finite = bool(torch.isfinite(torch.view_as_real(next(iter(out.values()))[:, -1])).all().item())
+host_bytes = sum(v.numel() * v.element_size() for v in host.values())
 if world > 1:
     t = torch.tensor([t_dev, t_all], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -55,6 +68,7 @@ if world > 1:
 if rank == 0:
     rec_steps = len(range(0, a.steps, a.every))
     print(json.dumps({"case": f"trajectory {a.steps} steps, {n}^2, {B} samples per GPU, every {a.every} steps, fields {fields}",
-                      "n_gpus": world, "global_batch": B * world, "snapshots": rec_steps, "result_shape": shape,
+                      "n_gpus": world, "global_batch": B * world, "snapshots": rec_steps, "result_shape_rank0": shape,
+                      "gather_to": a.gather_to, "physical": bool(a.physical), "subsample": a.subsample,
                       "seconds_device": t_dev, "steps_per_s_device": (a.steps - a.every + 1) / t_dev,
-                      "seconds_with_d2h": t_all, "finite": finite}))
+                      "seconds_end_to_end_host_result": t_all, "host_bytes_rank0": host_bytes, "finite": finite}))

@@ -94,6 +94,13 @@ def _worker(rank, world, port, q):
                                           record_every_steps=2, fields=("vorticity", "stream"))
         ref = O.trajectory(tb, w0, 1e-3, 5, 2)
         ok = all(torch.equal(out[k], ref[k]) for k in ("vorticity", "stream")) and set(out) == {"vorticity", "stream"}
+        # gather_to = None: every rank keeps its shard; gather_to = 1: only rank 1 receives the global result
+        mine = get_trajectory_imex_sharded(OracleEquation(tb), w0[rank * per:(rank + 1) * per], 1e-3, num_steps=5,
+                                           record_every_steps=2, fields=("vorticity",), gather_to=None)
+        ok = ok and torch.equal(mine["vorticity"], ref["vorticity"][rank * per:(rank + 1) * per])
+        one = get_trajectory_imex_sharded(OracleEquation(tb), w0[rank * per:(rank + 1) * per], 1e-3, num_steps=5,
+                                          record_every_steps=2, fields=("vorticity",), gather_to=1)
+        ok = ok and ((rank == 1 and torch.equal(one["vorticity"], ref["vorticity"])) or (rank != 1 and one == {}))
         q.put((rank, bool(ok), tuple(out["vorticity"].shape)))
     finally:
         dist.destroy_process_group()
