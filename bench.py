@@ -129,14 +129,48 @@ def make_state(n, batch, dtype, first_index):
     return w
 
 
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def reference_kind():
+    """"reference": the UNMODIFIED reference modules copied by oracle/make_ref.sh are present (oracle/_ref, git-ignored,
+    shipped by gpurun) and are what the CPU legs time; "port": the oracle restatement (pinned bit-exactly to the
+    reference by tests/test_oracle_cpu.py)."""
+    if os.path.isdir(os.path.join(REF_DIR, "torch_cfd")) and os.environ.get("TCFD_BENCH_PORT") != "1":
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        sys.dont_write_bytecode = True
+        return "reference"
+    return "port"
+
+
 def cpu_reference_steps_per_s(n, batch, dtype, steps, threads):
-    """The reference's CPU path (oracle port: same torch ops in the same order, pinned bit-exactly
-    to the reference by tests/test_oracle_cpu.py) on the host cores; 1 warm-up + `steps` timed."""
+    """The reference's CPU path on the host cores; 1 warm-up step + `steps` timed.  With oracle/_ref present this is
+    the reference's own NavierStokes2DSpectral + RK4CrankNicolsonStepper (torch_cfd/equations.py), else the oracle port."""
     from oracle import ns2d_oracle as O
     torch.set_num_threads(threads)
     diam = 2 * torch.pi
-    tb = O.make_tables(n, diam, VISC, DRAG, True, ("vorticity", O.kolmogorov_forcing_vorticity(n, diam, dtype)), dtype)
     w = make_state(n, batch, dtype, 0)
+    if reference_kind() == "reference":
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(dtype)
+        try:
+            from torch_cfd.grids import Grid
+            from torch_cfd.equations import NavierStokes2DSpectral, RK4CrankNicolsonStepper
+            from torch_cfd.forcings import KolmogorovForcing
+            grid = Grid(shape=(n, n), domain=((0, diam), (0, diam)))
+            ns = NavierStokes2DSpectral(viscosity=VISC, grid=grid, drag=DRAG, smooth=True,
+                                        forcing_fn=KolmogorovForcing(diam=diam, wave_number=1, grid=grid, scale=1, vorticity=True),
+                                        solver=RK4CrankNicolsonStepper())
+            with torch.no_grad():
+                w, _ = ns(w, DT, steps=1)
+                t0 = time.perf_counter()
+                w, _ = ns(w, DT, steps=steps)
+                el = time.perf_counter() - t0
+        finally:
+            torch.set_default_dtype(prev)
+        return steps / el, el
+    tb = O.make_tables(n, diam, VISC, DRAG, True, ("vorticity", O.kolmogorov_forcing_vorticity(n, diam, dtype)), dtype)
     with torch.no_grad():
         w, _ = O.forward(tb, w, DT, 1)
         t0 = time.perf_counter()
@@ -156,7 +190,9 @@ def run_reference(a):
     per, el1 = cpu_reference_steps_per_s(a.n, a.batch, dtype, 1, threads)
     k = max(1, min(k, int(60.0 * per)))
     v, el = cpu_reference_steps_per_s(a.n, a.batch, dtype, k, threads)
-    sample = f"{k} full steps of the {a.batch} x {a.n}^2 batch after 1 warm-up step, torch CPU, {threads} threads"
+    kind = reference_kind()
+    sample = (f"{k} full steps of the {a.batch} x {a.n}^2 batch after 1 warm-up step, "
+              f"{'reference modules (oracle/_ref)' if kind == 'reference' else 'oracle port'}, torch CPU, {threads} threads")
     unit = UNIT
     _emit(json.dumps({
         "impl": "reference", "metric": "rk4_spectral_steps_per_sec", "value": v, "unit": unit,
@@ -166,7 +202,7 @@ def run_reference(a):
         "config": {"workload": workload_name(a.n, a.batch, a.dtype),
                    "step": f"one RK4+CN step (5 substages) of {a.batch} x {a.n}^2 samples",
                    "note": "CPU arm: rank 0 only, one batch regardless of --gpus"},
-        "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -336,9 +372,11 @@ def run_ours(a):
     if not a.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         v, el = cpu_reference_steps_per_s(n, B, dtype, a.cpu_steps, threads)
-        out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
+        kind = reference_kind()
+        out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": kind,
                                "sample": f"{a.cpu_steps} full steps of the {B} x {n}^2 batch after 1 warm-up, "
-                                         f"oracle port of the reference (torch CPU), {el:.1f} s"}
+                                         f"{'reference modules (oracle/_ref)' if kind == 'reference' else 'oracle port of the reference'} "
+                                         f"(torch CPU), {el:.1f} s"}
     _emit(json.dumps(out))
 
 
@@ -411,13 +449,24 @@ def sconv_cpu(b, C, threads, batch_sample):
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     x = torch.randn(batch_sample, C, C4["X"], C4["Y"], C4["T"], requires_grad=True)
-    w = [(0.5 / (C * C) * torch.rand(C, C, 20, 20, 8, 2)).requires_grad_() for _ in range(4)]
     cot = torch.randn(batch_sample, C, C4["X"], C4["Y"], C4["T"])
+    if reference_kind() == "reference":
+        from fno.sfno import SpectralConvT as RefConvT
+        m = RefConvT(C, C, 20, 20, 8, out_steps=C4["T"], temporal_padding=True, bias=False)
 
-    def step():
-        y = SO.spectral_conv_t(x, w, 20, 20, 8, C4["T"], None, 0.1, True)
-        y.backward(cot)
-        x.grad = None
+        def step():
+            y = m(x)
+            y.backward(cot)
+            x.grad = None
+            for p_ in m.parameters():
+                p_.grad = None
+    else:
+        w = [(0.5 / (C * C) * torch.rand(C, C, 20, 20, 8, 2)).requires_grad_() for _ in range(4)]
+
+        def step():
+            y = SO.spectral_conv_t(x, w, 20, 20, 8, C4["T"], None, 0.1, True)
+            y.backward(cot)
+            x.grad = None
     step()
     t0 = time.perf_counter()
     step()
@@ -507,8 +556,8 @@ def run_sconv(a):
     if not a.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         v, el = sconv_cpu(b, C, threads, 1)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"forward + backward of 1 sample of the batch (oracle, torch CPU), scaled x{b}"}
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": reference_kind(),
+                               "sample": f"forward + backward of 1 sample of the batch ({reference_kind()}, torch CPU), scaled x{b}"}
     _emit(json.dumps(out))
 
 
@@ -518,12 +567,12 @@ def run_sconv_reference(a):
     threads = os.cpu_count() or 1
     nb = max(1, min(a.batch, 2))
     v, el = sconv_cpu(a.batch, a.width, threads, nb)
-    sample = f"forward + backward of {nb} samples of the batch (oracle port, torch CPU, {threads} threads), scaled to {a.batch}"
+    sample = f"forward + backward of {nb} samples of the batch ({reference_kind()}, torch CPU, {threads} threads), scaled to {a.batch}"
     _emit(json.dumps({
         "impl": "reference", "metric": "sconv_fwd_bwd_steps_per_sec", "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": 1,
         "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": sconv_workload_name(a.batch, a.width), "note": "CPU arm: rank 0 only"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": reference_kind(), "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -542,6 +591,15 @@ def fno3d_cpu(batch, C, threads, nb):
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     x = torch.randn(nb, C5["in_ch"], C5["X"], C5["Y"], C5["T"])
+    if reference_kind() == "reference":
+        from fno.fno3d import FNO3d as RefFNO3d
+        m = RefFNO3d(8, 8, 5, C, input_channel=10).eval()
+        with torch.no_grad():
+            m(x)
+            t0 = time.perf_counter()
+            m(x)
+            el = (time.perf_counter() - t0) * batch / nb
+        return 1.0 / el, el
     p = nn.Conv3d(13, C, 1)
     layers = [([torch.rand(C, C, 8, 8, 5, dtype=torch.cfloat) / (C * C) for _ in range(4)],
                nn.Conv3d(C, C, 1), nn.Conv3d(C, C, 1), nn.Conv3d(C, C, 1)) for _ in range(4)]
@@ -621,8 +679,8 @@ def run_fno3d(a):
     if not a.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         v, el = fno3d_cpu(B, C, threads, 2)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"forward of 2 samples (reference layer sequence, torch CPU), scaled x{B // 2}"}
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": reference_kind(),
+                               "sample": f"forward of 2 samples ({reference_kind()}: FNO3d layer sequence, torch CPU), scaled x{B // 2}"}
     _emit(json.dumps(out))
 
 
@@ -631,12 +689,12 @@ def run_fno3d_reference(a):
         return
     threads = os.cpu_count() or 1
     v, el = fno3d_cpu(a.batch, a.width, threads, 4)
-    sample = f"forward of 4 samples (reference layer sequence, torch CPU, {threads} threads), scaled to {a.batch}"
+    sample = f"forward of 4 samples ({reference_kind()}: FNO3d layer sequence, torch CPU, {threads} threads), scaled to {a.batch}"
     _emit(json.dumps({
         "impl": "reference", "metric": "fno3d_forward_steps_per_sec", "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": 1,
         "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": fno3d_workload_name(a.batch, a.width), "note": "CPU arm: rank 0 only"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": reference_kind(), "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
