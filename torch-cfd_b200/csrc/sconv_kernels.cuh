@@ -241,6 +241,52 @@ struct GroupSync {
   }
 };
 
+// Small dense complex product of one thread group (the t-axis table products of the plane kernels):
+//   out(i, c) = sum_k A[c * as + k] * V[i * vs + k]      i < NI rows, c < NC columns, k < NK   (shared memory operands)
+// Thread (pl, kl) -- pl = t % NP, kl = t / NP, NP = ceil(NC / 2), KL = NT / NP, computed once per kernel by the caller --
+// owns the column pair (2 pl, 2 pl + 1) and the rows kl, kl + KL, kl + 2 KL, ... in register tiles of RK rows: a
+// table entry it loads serves RK rows, an input entry two columns (2 + RK loads per 2 RK multiply-adds instead of 2
+// per multiply-add), the accumulators are packed (re, im) pairs (two FFMA2 per complex multiply-add), and no index
+// of the loop nest needs a division.  store(i, c, value) writes one result.
+template <int RK, class Store>
+TCFD_D void group_cproduct(const cx<float>* A, int as, const cx<float>* V, int vs, int NI, int NC, int NK, int pl, int kl, int KL,
+                           bool active, Store store) {
+  if (!active) return;
+  const int c0 = 2 * pl, c1 = c0 + 1;
+  const bool has1 = c1 < NC;
+  const cx<float>* a0p = A + (size_t)c0 * as;
+  const cx<float>* a1p = A + (size_t)(has1 ? c1 : c0) * as;
+  for (int i0 = kl; i0 < NI; i0 += KL * RK) {
+    f2 acc0[RK], acc1[RK];
+    const cx<float>* vp[RK];
+#pragma unroll
+    for (int r = 0; r < RK; ++r) {
+      acc0[r] = f2(0.f);
+      acc1[r] = f2(0.f);
+      const int i = i0 + r * KL;
+      vp[r] = V + (size_t)(i < NI ? i : i0) * vs;  // rows past the end repeat row i0 (results discarded)
+    }
+    for (int k = 0; k < NK; ++k) {
+      const cx<float> a0 = a0p[k], a1 = a1p[k];
+#pragma unroll
+      for (int r = 0; r < RK; ++r) {
+        const cx<float> v = vp[r][k];
+        const f2 v1(v.x, v.y), v2(-v.y, v.x);
+        acc0[r] = fma_rn(v2, a0.y, fma_rn(v1, a0.x, acc0[r]));
+        acc1[r] = fma_rn(v2, a1.y, fma_rn(v1, a1.x, acc1[r]));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RK; ++r) {
+      const int i = i0 + r * KL;
+      if (i < NI) {
+        store(i, c0, cx<float>{acc0[r].lo, acc0[r].hi});
+        if (has1) store(i, c1, cx<float>{acc1[r].lo, acc1[r].hi});
+      }
+    }
+  }
+}
+
 template <int Y>
 struct Planes2Smem {
   static constexpr int NT = Y / 8;
@@ -287,6 +333,9 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
   GroupSync<NT> sync{1 + g};
   int parity = 0;
   const bool teven = (T & 1) == 0;
+  // thread mapping of the register-tiled t-axis product (one division per kernel, none per plane)
+  const int NP = (mt + 1) / 2, KL = NT / (NP > 0 ? NP : 1), pl = t % NP, kl = t / NP;
+  const bool tiled = NP <= NT;
   for (int i = threadIdx.x; i < mt * T; i += blockDim.x) As[(i / T) * AS + i % T] = A[i];
   const int stride = (int)gridDim.x * GP;
   const int iters = (nplanes + stride - 1) / stride;
@@ -355,17 +404,23 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
     }
     if (valid) {
       cx<float>* dst = Z1 + (size_t)plane * NKY * mt;
-      for (int j = t; j < NKY * mt; j += NT) {
-        const int kyi = j / mt, kt = j % mt;
-        const cx<float>* xr = Xy + (size_t)kyi * XS;
-        const cx<float>* ar = As + (size_t)kt * AS;
-        float sr = 0.f, si = 0.f;
-        for (int tt = 0; tt < T; ++tt) {
-          const cx<float> a = ar[tt], v = xr[tt];
-          sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
-          si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
+      if (tiled) {
+        // t-axis analysis: Z1[kyi][kt] = sum_tt A[kt][tt] Xy[kyi][tt], register-tiled (group_cproduct)
+        group_cproduct<4>(As, AS, Xy, XS, NKY, mt, T, pl, kl, KL, kl < KL,
+                          [&](int kyi, int kt, cx<float> v) { dst[(size_t)kyi * mt + kt] = v; });
+      } else {
+        for (int j = t; j < NKY * mt; j += NT) {
+          const int kyi = j / mt, kt = j % mt;
+          const cx<float>* xr = Xy + (size_t)kyi * XS;
+          const cx<float>* ar = As + (size_t)kt * AS;
+          float sr = 0.f, si = 0.f;
+          for (int tt = 0; tt < T; ++tt) {
+            const cx<float> a = ar[tt], v = xr[tt];
+            sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
+            si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
+          }
+          dst[j] = cx<float>{sr, si};
         }
-        dst[j] = cx<float>{sr, si};
       }
     }
     sync();  // Xy / Es are re-used by the next plane
@@ -395,6 +450,9 @@ sconv_planes_inv2_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
   GroupSync<NT> sync{1 + g};
   int parity = 0;
   const bool teven = (T & 1) == 0;
+  // thread mapping of the register-tiled t-axis product: column pairs are pairs of output time samples here
+  const int NP = (T + 1) / 2, KL = NT / (NP > 0 ? NP : 1), pl = t % NP, kl = t / NP;
+  const bool tiled = NP <= NT;
   for (int i = threadIdx.x; i < mt * T; i += blockDim.x) Ss[(i / mt) * SS + i % mt] = Sy[i];
   const int stride = (int)gridDim.x * GP;
   const int iters = (nplanes + stride - 1) / stride;
@@ -415,19 +473,28 @@ sconv_planes_inv2_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
     tile_load_wait(bar, (unsigned)(it & 1));
     // t-axis synthesis on the kept ky:  D[kyi][t] = sum_kt Sy[t][kt] Z2[kyi][kt]   (complex)
     const cx<float>* src = reinterpret_cast<const cx<float>*>(zin);
-    for (int j = t; j < NKY * TQ * 4; j += NT) {
-      const int kyi = j / (TQ * 4), tt = j % (TQ * 4);
-      float sr = 0.f, si = 0.f;
-      if (tt < T) {
-        const cx<float>* zr = src + (size_t)kyi * mt;
-        const cx<float>* sy = Ss + (size_t)tt * SS;
-        for (int kt = 0; kt < mt; ++kt) {
-          const cx<float> a = sy[kt], v = zr[kt];
-          sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
-          si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
+    if (tiled) {
+      // D[kyi][tt] = sum_kt Sy[tt][kt] Z2[kyi][kt], register-tiled (group_cproduct); the padding entries tt in [T, 4 TQ) stay 0
+      group_cproduct<4>(Ss, SS, src, mt, NKY, T, mt, pl, kl, KL, kl < KL,
+                        [&](int kyi, int tt, cx<float> v) { D[(size_t)kyi * XS + tt] = v; });
+      if (T < TQ * 4)
+        for (int kyi = t; kyi < NKY; kyi += NT)
+          for (int tt = T; tt < TQ * 4; ++tt) D[(size_t)kyi * XS + tt] = cx<float>{0.f, 0.f};
+    } else {
+      for (int j = t; j < NKY * TQ * 4; j += NT) {
+        const int kyi = j / (TQ * 4), tt = j % (TQ * 4);
+        float sr = 0.f, si = 0.f;
+        if (tt < T) {
+          const cx<float>* zr = src + (size_t)kyi * mt;
+          const cx<float>* sy = Ss + (size_t)tt * SS;
+          for (int kt = 0; kt < mt; ++kt) {
+            const cx<float> a = sy[kt], v = zr[kt];
+            sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
+            si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
+          }
         }
+        D[(size_t)kyi * XS + tt] = cx<float>{sr, si};
       }
-      D[(size_t)kyi * XS + tt] = cx<float>{sr, si};
     }
     sync();  // D complete, zin consumed
     if (t == 0) {
