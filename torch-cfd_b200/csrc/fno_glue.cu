@@ -411,7 +411,7 @@ extern "C" int tcfd_fno_layer_glue(const float* conv_out, const float* x, float*
       const bool tail = npts % 128 != 0;
       // dynamic shared memory only pads the footprint so that the resident CTAs of an SM never ask for more than
       // the 512 TMEM columns: 4 CTAs (128 columns each) for C <= 24, 2 CTAs (256 columns) above
-      const int per_sm = C <= 24 ? 4 : 2;
+      const int per_sm = C <= 24 ? TCFD_GLUE_MINB : 2;
       const size_t pad = C <= 24 ? 30 * 1024 : 64 * 1024;
       const size_t grid = ntiles < (size_t)sms * per_sm ? ntiles : (size_t)sms * per_sm;
 #define TCFD_GLUE_TC_RUN(cc, tl, sw_)                                                                                  \

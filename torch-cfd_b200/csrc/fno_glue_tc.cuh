@@ -18,8 +18,9 @@
 //   * every thread reads its accumulator row back (tcgen05.ld), adds the bias, applies the erf-form GELU (the only
 //     arithmetic left on the CUDA cores), and either feeds the result back as the A operand of the second product
 //     or writes the output channel planes.
-// TMEM budget per CTA: 32 accumulator columns + 2 x (2 KP) operand columns (KP = C padded to 8) = 128 for C <= 24
-// (4 CTAs per SM), 256 for C <= 32 (2 CTAs per SM).
+// TMEM budget per CTA: 32 accumulator columns + 2 x (2 KP) operand columns (KP = C padded to 8) = 128 for C <= 24,
+// 256 for C <= 32.  Resident CTAs per SM: 3 for C <= 24 (80 registers, no spills: measured 1.37 ms per C5 layer
+// against 1.66 ms with 4 CTAs at 64 registers and 1.51 ms with 2), 2 above.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -27,6 +28,9 @@
 namespace tcfd {
 namespace gluetc {
 
+#ifndef TCFD_GLUE_MINB
+#define TCFD_GLUE_MINB 3
+#endif
 constexpr int NP = 32;  // accumulator columns = UMMA N (outputs padded to 32)
 
 template <int KP>
@@ -191,7 +195,7 @@ __device__ __forceinline__ void tmem_ld(unsigned taddr, float* v) {
 // tile's products are waited for.  TAIL: the number of points per sample is not a multiple of 128 (predicated
 // accesses).  SWAP: exchange the two descriptor strides (bring-up knob: gives garbage).
 template <int C, bool TAIL, bool SWAP>
-__global__ void __launch_bounds__(256, (C <= 24 ? 4 : 2))
+__global__ void __launch_bounds__(256, (C <= 24 ? TCFD_GLUE_MINB : 2))
 fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ x, float* __restrict__ y,
                          const __grid_constant__ TcWeights<(C + 7) / 8 * 8> W, int act, size_t npts, size_t tiles_per_sample,
                          size_t ntiles) {
