@@ -51,6 +51,9 @@ def test_emu_sconv_vs_reference_golden(tag, kind, cfg):
     ((2, 3, 32, 64, 9), (5, 7, 4), dict()),                                      # odd T
     ((1, 2, 64, 32, 12), (32, 16, 7), dict(bias=True, delta=0.3)),                # mx = X/2, my = Y/2 (full)
     ((1, 2, 32, 32, 4), (3, 3, 5), dict(t_pad=4, T_out=9, bias=True, norm="forward")),
+    ((1, 2, 32, 128, 6), (4, 20, 4), dict()),                                     # pruned y inverse, my = 20 twiddles
+    ((1, 1, 32, 64, 4), (3, 24, 2), dict(bias=True)),                             # ... my in (20, 32]
+    ((1, 1, 32, 64, 5), (3, 12, 3), dict()),                                      # ... my in (8, 16], odd mt (one copy)
 ])
 def test_emu_sconv_vs_oracle(shape, modes, kw):
     torch.manual_seed(3)

@@ -59,7 +59,8 @@ def test_modules_vs_reference_golden(tag, kind, cfg):
             assert rel_l2(p.grad, ref) < tol
 
 
-@pytest.mark.parametrize("X,Y,T,modes", [(64, 128, 10, (12, 20, 6)), (256, 64, 16, (20, 8, 8)), (128, 128, 7, (8, 8, 4))])
+@pytest.mark.parametrize("X,Y,T,modes", [(64, 128, 10, (12, 20, 6)), (256, 64, 16, (20, 8, 8)), (128, 128, 7, (8, 8, 4)),
+                                            (64, 256, 10, (6, 28, 6)), (32, 64, 6, (4, 12, 4)), (32, 512, 4, (4, 20, 3))])
 def test_modules_vs_oracle_sizes(X, Y, T, modes):
     from torch_cfd_b200.fno import SpectralConvS
     torch.manual_seed(5)

@@ -111,14 +111,16 @@ int planes_grid(const void* kernel, int threads, size_t smem, int want) {
   return want < 3 ? want : 3;  // several planes per group: exercises the double buffering
 #endif
 }
-bool planes_v1() {
+// TCFD_SCONV_PLANES = 1 / 2: force the first / second generation plane kernels (bring-up and A/B timing)
+int planes_gen() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TCFD_SCONV_PLANES");
-    v = (e && atoi(e) == 1) ? 1 : 0;
+    v = e ? atoi(e) : 0;
   }
-  return v == 1;
+  return v;
 }
+bool planes_v1() { return planes_gen() == 1; }
 template <int Y>
 int launch_planes_fwd2(const float* x, cplx* Z1, const cplx* A, const cplx* tw, SconvDims d, int nplanes, cudaStream_t st) {
   typedef Planes2Smem<Y> S;
@@ -142,6 +144,27 @@ int launch_planes_inv2(const cplx* Z2, float* y, const cplx* Sy, const cplx* tw,
   TCFD_LAUNCH(k, grid, S::GP * S::NT, smem, st, Z2, y, Sy, tw, d, nplanes);
   return 0;
 }
+// third generation (inverse only): pruned y transform without exchanges; MYT = compile-time bound of my
+template <int Y, int MYT>
+int launch_planes_inv3(const cplx* Z2, float* y, const cplx* Sy, const cplx* tw, SconvDims d, int nplanes, cudaStream_t st) {
+  typedef Planes3Smem<Y> S;
+  const size_t smem = S::table_bytes(d.Tout, d.mt) + S::GP * S::group_bytes(d.Tout, d.my, d.mt);
+  if (smem > 227 * 1024 || (reinterpret_cast<uintptr_t>(y) & 15u) || (reinterpret_cast<uintptr_t>(Z2) & 15u))
+    return launch_planes_inv2<Y>(Z2, y, Sy, tw, d, nplanes, st);
+  auto k = sconv_planes_inv3_kernel<Y, MYT>;
+  if (int rc = set_smem(k, smem)) return rc;
+  const int grid = planes_grid(reinterpret_cast<const void*>(k), S::GP * S::NT, smem, (nplanes + S::GP - 1) / S::GP);
+  TCFD_LAUNCH(k, grid, S::GP * S::NT, smem, st, Z2, y, Sy, tw, d, nplanes);
+  return 0;
+}
+template <int Y>
+int launch_planes_inv_best(const cplx* Z2, float* y, const cplx* Sy, const cplx* tw, SconvDims d, int nplanes, cudaStream_t st) {
+  if (planes_gen() == 2 || d.my > 32 || 2 * d.my + 1 > Y) return launch_planes_inv2<Y>(Z2, y, Sy, tw, d, nplanes, st);
+  if (d.my <= 8) return launch_planes_inv3<Y, 8>(Z2, y, Sy, tw, d, nplanes, st);
+  if (d.my <= 16) return launch_planes_inv3<Y, 16>(Z2, y, Sy, tw, d, nplanes, st);
+  if (d.my <= 20) return launch_planes_inv3<Y, 20>(Z2, y, Sy, tw, d, nplanes, st);
+  return launch_planes_inv3<Y, 32>(Z2, y, Sy, tw, d, nplanes, st);
+}
 template <int X, bool FWD>
 int launch_xaxis(const cplx* in, cplx* out, const cplx* tw, SconvDims d, int ncol, int nslabs, cudaStream_t st) {
   typedef XaxisSmem<X> S;
@@ -161,7 +184,7 @@ int planes_fwd(int Y, const float* x, cplx* Z1, const cplx* A, const cplx* tw, S
   return -1;
 }
 int planes_inv(int Y, const cplx* Z2, float* y, const cplx* Sy, const cplx* tw, SconvDims d, int np, cudaStream_t st) {
-#define CASE(n) if (Y == n) return planes_v1() ? launch_planes_inv<n>(Z2, y, Sy, tw, d, np, st) : launch_planes_inv2<n>(Z2, y, Sy, tw, d, np, st);
+#define CASE(n) if (Y == n) return planes_v1() ? launch_planes_inv<n>(Z2, y, Sy, tw, d, np, st) : launch_planes_inv_best<n>(Z2, y, Sy, tw, d, np, st);
   SCONV_SIZES(CASE)
 #undef CASE
   return -1;

@@ -548,6 +548,184 @@ sconv_planes_inv2_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
 }
 
 // ------------------------------------------------------------------------------------------
+// Third-generation inverse plane kernel: the y-axis inverse as a PRUNED transform without shared-memory exchanges.
+// Only the 2 my + 1 frequencies |k| <= my of the Y inputs are non-zero.  With Y = 8 NT and n = t + NT h:
+//     y[t + NT h] = sum_b e^{+2 pi i b h / 8} U_t[b],      U_t[b] = sum_{|k| <= my, k = b (mod 8)} X[k] e^{+2 pi i k t / Y}
+// so thread t accumulates its eight U_t[b] from broadcast reads of the 2 my + 1 inputs (its twiddles e^{2 pi i j t / Y},
+// j = 1..my, live in registers; negative k take the conjugates) and one radix-8 butterfly in registers yields the
+// same eight rows t + m NT the full transform leaves in the thread.  Against the Stockham transform (two exchanges =
+// 128 shared-memory wavefronts per packed transform) this reads 2 my + 1 broadcast entries (one wavefront each) for a
+// similar number of packed multiply-adds; measured with ncu the second-generation kernel kept the shared-memory
+// data pipe 78 % busy (profiles/r2h_*).  The truncated spectrum block is staged row by row into rows padded to an
+// even stride that spreads the rows a warp reads at once over the banks (mt even; odd mt keeps one contiguous copy).
+template <int Y>
+struct Planes3Smem {
+  static constexpr int NT = Y / 8;
+  static constexpr int GP = (64 / NT) > 0 ? (64 / NT) : 1;
+  TCFD_HD static int tq(int T) { return (T + 3) / 4; }
+  TCFD_HD static int xs(int T) { return tq(T) * 4 + 1; }
+  TCFD_HD static int ts(int n) { return n | 1; }
+  TCFD_HD static int zs(int mt) { return (mt & 1) ? mt : mt + 2; }  // padded row of the staged spectrum block (entries)
+  TCFD_HD static size_t a16(size_t b) { return (b + 15) / 16 * 16; }
+  TCFD_HD static size_t tile_bytes(int T) { return a16((size_t)Y * T * 4); }
+  TCFD_HD static size_t dh_bytes(int my) { return (size_t)(2 * my + 1) * 16; }
+  TCFD_HD static size_t zin_bytes(int my, int mt) { return a16((size_t)2 * my * zs(mt) * 8); }
+  // group: tile | Dh | D | zin | barrier  (C4: 18.3 KB -> six CTAs of two groups per SM)
+  TCFD_HD static size_t group_bytes(int T, int my, int mt) {
+    return a16(tile_bytes(T) + dh_bytes(my) + a16((size_t)(2 * my) * xs(T) * 8) + zin_bytes(my, mt) + 16);
+  }
+  TCFD_HD static size_t table_bytes(int T, int mt) { return a16((size_t)T * ts(mt) * 8); }
+};
+
+// U[b] += sum over the kept frequencies; Dh: entries k = 0..my, then k = -my..-1 (the layout of the Hermitian step)
+template <int MYT>
+TCFD_D void pruned_inverse_y(const cx<f2>* Dh, int my, const cx<float> (&w)[MYT], cx<f2> (&z)[8]) {
+#pragma unroll
+  for (int b = 1; b < 8; ++b) z[b] = cx<f2>{f2(0.f), f2(0.f)};
+  z[0] = Dh[0];
+#pragma unroll
+  for (int j = 1; j <= MYT; ++j) {
+    if (j > my) break;  // group-uniform
+    const int bp = j & 7, bn = (8 - (j & 7)) & 7;  // compile-time after unrolling
+    const cx<f2> xp = Dh[j], xn = Dh[2 * my + 1 - j];
+    const cx<float> wj = w[j - 1];
+    // xp * w
+    z[bp].x = fma_rn(xp.y, -wj.y, fma_rn(xp.x, wj.x, z[bp].x));
+    z[bp].y = fma_rn(xp.y, wj.x, fma_rn(xp.x, wj.y, z[bp].y));
+    // xn * conj(w)
+    z[bn].x = fma_rn(xn.y, wj.y, fma_rn(xn.x, wj.x, z[bn].x));
+    z[bn].y = fma_rn(xn.x, -wj.y, fma_rn(xn.y, wj.x, z[bn].y));
+  }
+  radix8<+1>(z);
+}
+
+template <int Y, int MYT>
+__global__ void __launch_bounds__(Planes3Smem<Y>::GP * (Y / 8))
+sconv_planes_inv3_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y, const cx<float>* __restrict__ Sy,
+                         const cx<float>* __restrict__ twtab, SconvDims d, int nplanes) {
+  typedef Planes3Smem<Y> S;
+  constexpr int NT = S::NT, GP = S::GP;
+  const int T = d.Tout, my = d.my, mt = d.mt, NKY = 2 * my, TQ = S::tq(T), XS = S::xs(T), SS = S::ts(mt), ZS = S::zs(mt);
+  TCFD_DYN_SMEM(smem_raw);
+  const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+  cx<float>* Ss = reinterpret_cast<cx<float>*>(smem_raw);  // [T][mt], CTA-shared
+  unsigned char* base = smem_raw + S::table_bytes(T, mt) + (size_t)g * S::group_bytes(T, my, mt);
+  float* tile = reinterpret_cast<float*>(base);
+  cx<f2>* Dh0 = reinterpret_cast<cx<f2>*>(base + S::tile_bytes(T));
+  cx<float>* D = reinterpret_cast<cx<float>*>(Dh0 + (2 * my + 1));  // [NKY][XS]
+  unsigned char* zin = reinterpret_cast<unsigned char*>(D) + S::a16((size_t)NKY * XS * 8);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(zin + S::zin_bytes(my, mt));
+  GroupSync<NT> sync{1 + g};
+  // e^{+2 pi i j t / Y}, j = 1..MYT (the table holds the forward sign)
+  cx<float> w[MYT];
+#pragma unroll
+  for (int j = 1; j <= MYT; ++j) w[j - 1] = conj(twtab[(j * t) & (Y - 1)]);
+  const bool teven = (T & 1) == 0;
+  const bool rowcopy = (mt & 1) == 0;
+  const int NP = (T + 1) / 2, KL = NT / (NP > 0 ? NP : 1), pl = t % NP, kl = t / NP;
+  const bool tiled = NP <= NT;
+  for (int i = threadIdx.x; i < mt * T; i += blockDim.x) Ss[(i / mt) * SS + i % mt] = Sy[i];
+  const int stride = (int)gridDim.x * GP;
+  const int iters = (nplanes + stride - 1) / stride;
+  auto plane_of = [&](int it) { return (it * (int)gridDim.x + (int)blockIdx.x) * GP + g; };
+  // staging of a spectrum block: even mt -- every thread copies 16-byte pieces into the padded rows (LDGSTS, completion
+  // by wait_group + the group barrier); odd mt -- one contiguous bulk copy by thread 0 (mbarrier completion)
+  const int upr = mt >> 1;  // 16-byte units per row (even mt)
+  auto stage_block = [&](int it) {
+    int p = plane_of(it);
+    if (p >= nplanes) p = nplanes - 1;
+    const cx<float>* src = Z2 + (size_t)p * NKY * mt;
+    if (rowcopy) {
+      for (int u = t; u < NKY * upr; u += NT) {
+        const int row = u / upr, wi = u - row * upr;
+        ldgsts16(zin + (size_t)row * ZS * 8 + wi * 16, reinterpret_cast<const unsigned char*>(src) + (size_t)u * 16);
+      }
+      ldgsts_commit();
+    } else if (t == 0) {
+      stage_expect(bar, (unsigned)((size_t)NKY * mt * 8));
+      bulk_load(zin, src, (unsigned)((size_t)NKY * mt * 8), bar);
+    }
+  };
+  if (t == 0) stage_barrier_init(bar);
+  __syncthreads();
+  if (iters > 0) stage_block(0);
+
+  for (int it = 0; it < iters; ++it) {
+    const int plane = plane_of(it);
+    const bool valid = plane < nplanes;
+    if (rowcopy) {
+      ldgsts_wait_all();
+      sync();
+    } else {
+      tile_load_wait(bar, (unsigned)(it & 1));
+    }
+    const cx<float>* src = reinterpret_cast<const cx<float>*>(zin);
+    if (tiled) {
+      group_cproduct<4>(Ss, SS, src, ZS, NKY, T, mt, pl, kl, KL, kl < KL,
+                        [&](int kyi, int tt, cx<float> v) { D[(size_t)kyi * XS + tt] = v; });
+      if (T < TQ * 4)
+        for (int kyi = t; kyi < NKY; kyi += NT)
+          for (int tt = T; tt < TQ * 4; ++tt) D[(size_t)kyi * XS + tt] = cx<float>{0.f, 0.f};
+    } else {
+      for (int j = t; j < NKY * TQ * 4; j += NT) {
+        const int kyi = j / (TQ * 4), tt = j % (TQ * 4);
+        float sr = 0.f, si = 0.f;
+        if (tt < T) {
+          const cx<float>* zr = src + (size_t)kyi * ZS;
+          const cx<float>* sy = Ss + (size_t)tt * SS;
+          for (int kt = 0; kt < mt; ++kt) {
+            const cx<float> a = sy[kt], v = zr[kt];
+            sr = fmaf(a.x, v.x, sr); sr = fmaf(-a.y, v.y, sr);
+            si = fmaf(a.x, v.y, si); si = fmaf(a.y, v.x, si);
+          }
+        }
+        D[(size_t)kyi * XS + tt] = cx<float>{sr, si};
+      }
+    }
+    if (t == 0) bulk_store_wait_read<0>();  // the previous plane's store has read the tile (first written after the next barrier)
+    sync();  // D complete, zin consumed
+    if (it + 1 < iters) stage_block(it + 1);  // the next block is staged under this plane's transforms
+    for (int q = 0; q < TQ; ++q) {
+      cx<f2>* Dh = Dh0;
+      if (q > 0) sync();  // the previous quad's reads of Dh
+      for (int e = t; e < 2 * my + 1; e += NT) {
+        const int ky = e <= my ? e : Y - my + (e - my - 1);
+        const int kn = (Y - ky) % Y;
+        const int i1 = kept_index(ky, Y, my), i2 = kept_index(kn, Y, my);
+        cx<float> h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const cx<float> a = i1 >= 0 ? D[(size_t)i1 * XS + 4 * q + j] : cx<float>{0.f, 0.f};
+          const cx<float> b = i2 >= 0 ? D[(size_t)i2 * XS + 4 * q + j] : cx<float>{0.f, 0.f};
+          h[j] = cx<float>{0.5f * (a.x + b.x), 0.5f * (a.y - b.y)};
+        }
+        Dh[e] = cx<f2>{f2(h[0].x - h[1].y, h[2].x - h[3].y), f2(h[0].y + h[1].x, h[2].y + h[3].x)};
+      }
+      sync();
+      cx<f2> z[8];
+      pruned_inverse_y<MYT>(Dh, my, w, z);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        float* r = tile + (t + m * NT) * T + 4 * q;
+        if (teven) {
+          *reinterpret_cast<cx<float>*>(r) = cx<float>{z[m].x.lo, z[m].y.lo};
+          if (4 * q + 2 < T) *reinterpret_cast<cx<float>*>(r + 2) = cx<float>{z[m].x.hi, z[m].y.hi};
+        } else {
+          r[0] = z[m].x.lo;
+          if (4 * q + 1 < T) r[1] = z[m].y.lo;
+          if (4 * q + 2 < T) r[2] = z[m].x.hi;
+          if (4 * q + 3 < T) r[3] = z[m].y.hi;
+        }
+      }
+    }
+    fence_async_smem();  // this thread's tile writes -> visible to the bulk store
+    sync();              // also: every thread has finished reading Dh / D of this plane
+    if (valid && t == 0) bulk_store(y + (size_t)plane * Y * T, tile, (unsigned)((size_t)Y * T * 4));
+  }
+  if (t == 0) bulk_store_wait_read<0>();  // shared memory must outlive the reads of the last store
+}
+
+// ------------------------------------------------------------------------------------------
 // x-axis transforms on column pairs.  In: FWD  Z [bc][X][ncol]  ->  Xh [bc][2mx][ncol] (kept kx)
 //                                      INV  Yh [bc][2mx][ncol] ->  Z  [bc][X][ncol]  (zero padded)
 // CTA = GP groups of NT = X/8 threads; group g transforms column pair (blockIdx.x * GP + g) of slab

@@ -114,6 +114,27 @@ TCFD_D void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long 
   std::memcpy(dst, src, bytes);
 #endif
 }
+// Per-thread asynchronous 16-byte copy global -> shared (SASS: LDGSTS, L2 only): unlike the bulk copies every lane has
+// its own source and destination, so a scattered destination layout (padded rows) costs one instruction per 16 bytes
+// of a thread instead of one warp-serialised UBLKCP per piece.  Completion: ldgsts_wait_all() by the issuing thread,
+// then a barrier with the readers.
+TCFD_D void ldgsts16(void* dst, const void* src) {
+#ifndef TCFD_EMU
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(src)) : "memory");
+#else
+  std::memcpy(dst, src, 16);
+#endif
+}
+TCFD_D void ldgsts_commit() {
+#ifndef TCFD_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+TCFD_D void ldgsts_wait_all() {
+#ifndef TCFD_EMU
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
 // 1-D bulk copy shared -> global (SASS: UBLKCP ... bulk_group), committed as one group.  The writers
 // of the shared source must have executed fence_async_smem() and synchronised with the issuing thread.
 TCFD_D void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
