@@ -175,6 +175,49 @@ int launch_xaxis(const cplx* in, cplx* out, const cplx* tw, SconvDims d, int nco
   return 0;
 }
 
+// second-generation x-axis kernels (persistent, prefetching); TCFD_SCONV_XAXIS = 1 forces the first generation
+int xaxis_gen() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TCFD_SCONV_XAXIS");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+template <int X>
+int launch_xaxis_fwd2(const cplx* in, cplx* out, const cplx* tw, SconvDims d, int ncol, int nslabs, cudaStream_t st) {
+  typedef Xaxis2Smem<X> S;
+  auto k = sconv_xaxis_fwd2_kernel<X>;
+  if (int rc = set_smem(k, S::FWD_BYTES)) return rc;
+  const int ntx = (ncol / 2 + S::GP - 1) / S::GP, ntiles = ntx * nslabs;
+  const int grid = planes_grid(reinterpret_cast<const void*>(k), S::GP * S::NT, S::FWD_BYTES, ntiles);
+  TCFD_LAUNCH(k, grid, S::GP * S::NT, S::FWD_BYTES, st, in, out, tw, d, ncol, ntx, ntiles);
+  return 0;
+}
+template <int X, int MXT>
+int launch_xaxis_inv2(const cplx* in, cplx* out, const cplx* tw, SconvDims d, int ncol, int nslabs, cudaStream_t st) {
+  typedef Xaxis2Smem<X> S;
+  auto k = sconv_xaxis_inv2_kernel<X, MXT>;
+  const size_t smem = S::inv_bytes(d.mx);
+  if (int rc = set_smem(k, smem)) return rc;
+  const int ntx = (ncol / 2 + S::GP - 1) / S::GP, ntiles = ntx * nslabs;
+  const int grid = planes_grid(reinterpret_cast<const void*>(k), S::GP * S::NT, smem, ntiles);
+  TCFD_LAUNCH(k, grid, S::GP * S::NT, smem, st, in, out, tw, d, ncol, ntx, ntiles);
+  return 0;
+}
+template <int X>
+int launch_xaxis_best(bool fwd, const cplx* in, cplx* out, const cplx* tw, SconvDims d, int ncol, int nslabs, cudaStream_t st) {
+  const bool aligned = !((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) && (ncol % 2) == 0;
+  if (xaxis_gen() == 1 || !aligned || (long long)((ncol / 2 + 7) / 8) * nslabs > 0x3fffffffLL)
+    return fwd ? launch_xaxis<X, true>(in, out, tw, d, ncol, nslabs, st) : launch_xaxis<X, false>(in, out, tw, d, ncol, nslabs, st);
+  if (fwd) return launch_xaxis_fwd2<X>(in, out, tw, d, ncol, nslabs, st);
+  if (d.mx > 32 || 2 * d.mx > X) return launch_xaxis<X, false>(in, out, tw, d, ncol, nslabs, st);
+  if (d.mx <= 8) return launch_xaxis_inv2<X, 8>(in, out, tw, d, ncol, nslabs, st);
+  if (d.mx <= 16) return launch_xaxis_inv2<X, 16>(in, out, tw, d, ncol, nslabs, st);
+  if (d.mx <= 20) return launch_xaxis_inv2<X, 20>(in, out, tw, d, ncol, nslabs, st);
+  return launch_xaxis_inv2<X, 32>(in, out, tw, d, ncol, nslabs, st);
+}
+
 #define SCONV_SIZES(F) F(32) F(64) F(128) F(256) F(512)
 
 int planes_fwd(int Y, const float* x, cplx* Z1, const cplx* A, const cplx* tw, SconvDims d, int np, cudaStream_t st) {
@@ -190,9 +233,7 @@ int planes_inv(int Y, const cplx* Z2, float* y, const cplx* Sy, const cplx* tw, 
   return -1;
 }
 int xaxis(int X, bool fwd, const cplx* in, cplx* out, const cplx* tw, SconvDims d, int ncol, int nslabs, cudaStream_t st) {
-#define CASE(n)                                                                       \
-  if (X == n) return fwd ? launch_xaxis<n, true>(in, out, tw, d, ncol, nslabs, st)    \
-                         : launch_xaxis<n, false>(in, out, tw, d, ncol, nslabs, st);
+#define CASE(n) if (X == n) return launch_xaxis_best<n>(fwd, in, out, tw, d, ncol, nslabs, st);
   SCONV_SIZES(CASE)
 #undef CASE
   return -1;
@@ -296,6 +337,44 @@ extern "C" size_t tcfd_sconv3d_xhat_elems(const tcfd_sconv3d_t* h, int batch) {
 extern "C" int tcfd_sconv3d_last_launch_count(const tcfd_sconv3d_t* h) { return h ? h->launches : 0; }
 
 namespace {
+// TCFD_SCONV_MIX = 1: first-generation mode-mixing kernels everywhere, 2: second generation everywhere (A/B timing)
+int mix_gen() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TCFD_SCONV_MIX");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+// Yh = Xh x W (BWD = false) or gXh = gYh x conj(W)^T (BWD = true)
+template <bool BWD>
+int launch_mix2(tcfd_sconv3d* h, const cplx* in, cplx* out, const MixArgs& a, const SconvDims& dm, int batch, cudaStream_t st) {
+  const int P = BWD ? a.Co : a.Ci, Q = BWD ? a.Ci : a.Co;
+  const int bt = (batch + MIX_BT - 1) / MIX_BT;
+  const int warps = (Q + MIX_OT - 1) / MIX_OT;
+  const size_t smem = (size_t)MIX_BT * P * 32 * sizeof(cplx);
+  // measured at C4 (profiles/r2i_*): the shared-tile kernel wins for the adjoint product (233 -> 102 us) but not for the
+  // forward one (113 vs 126 us), which keeps the first-generation kernel unless TCFD_SCONV_MIX = 2
+  const bool gen1 = mix_gen() == 1 || (!BWD && mix_gen() != 2);
+  if (gen1 || (h->K & 1) || warps > 8 || smem > 160 * 1024) {
+    // enough CTAs for every SM: split the batch tiles over grid.z when modes x channel tiles alone are few
+    const int gx = (h->K + 127) / 128, gy = warps;
+    int gz = 1184 / (gx * gy);
+    gz = gz < 1 ? 1 : (gz > bt ? bt : gz);
+    if (BWD) TCFD_LAUNCH3(sconv_mix_bwd_x_kernel, gx, gy, gz, 128, 0, st, in, out, a, dm);
+    else TCFD_LAUNCH3(sconv_mix_fwd_kernel, gx, gy, gz, 128, 0, st, in, out, a, dm);
+    return 0;
+  }
+  auto k = sconv_mix2_kernel<BWD>;
+  if (int rc = set_smem(k, smem)) return rc;
+  // one wave of co-resident CTAs: the batch tiles are split over grid.y only as far as the SMs have room
+  const int gx = (h->K + 31) / 32;
+  const int cap = planes_grid(reinterpret_cast<const void*>(k), warps * 32, smem, 1 << 30);
+  int gy = cap / gx;
+  gy = gy < 1 ? 1 : (gy > bt ? bt : gy);
+  TCFD_LAUNCH3(k, gx, gy, 1, warps * 32, smem, st, in, out, a, dm);
+  return 0;
+}
 // analysis half: x -> truncated spectrum Xh (kept for backward when xhat_save is given) -> per-mode channel mix -> Yh
 int analysis_impl(tcfd_sconv3d* h, const void* x, const void* const* w, const void* const* bias, float delta, cplx* Yh,
                   void* xhat_save, int batch, cudaStream_t st) {
@@ -316,13 +395,7 @@ int analysis_impl(tcfd_sconv3d* h, const void* x, const void* const* w, const vo
     a.bias[c] = bias ? static_cast<const cplx*>(bias[c]) : nullptr;
   }
   a.B = batch; a.Ci = d.Ci; a.Co = d.Co; a.delta = delta;
-  {
-    // enough CTAs for every SM: split the batch tiles over grid.z when modes x channel tiles alone are few
-    const int gx = (h->K + 127) / 128, gy = (d.Co + MIX_OT - 1) / MIX_OT, bt = (batch + MIX_BT - 1) / MIX_BT;
-    int gz = 1184 / (gx * gy);
-    gz = gz < 1 ? 1 : (gz > bt ? bt : gz);
-    TCFD_LAUNCH3(sconv_mix_fwd_kernel, gx, gy, gz, 128, 0, st, Xh, Yh, a, dm);
-  }
+  if (int rc2 = launch_mix2<false>(h, Xh, Yh, a, dm, batch, st)) return rc2;
   return check_launch(h, 0, "mix_fwd");
 }
 // synthesis half: truncated spectrum Yh (batch, Co, 2mx, 2my, mt) -> y
@@ -367,14 +440,15 @@ int analysis_bwd_impl(tcfd_sconv3d* h, const cplx* gYh, const void* xhat, const 
   if (grad_w) {
     for (int c = 0; c < 4; ++c)
       if (!grad_w[c]) return sfail(TCFD_ERR_INVALID, "null grad_w pointer");
-    TCFD_LAUNCH3(sconv_mix_bwd_w_kernel, (h->K + 127) / 128, d.Co, d.Ci, 128, 0, st, static_cast<const cplx*>(xhat), gYh, a, dm);
+    if (mix_gen() == 1)
+      TCFD_LAUNCH3(sconv_mix_bwd_w_kernel, (h->K + 127) / 128, d.Co, d.Ci, 128, 0, st, static_cast<const cplx*>(xhat), gYh, a, dm);
+    else
+      TCFD_LAUNCH3(sconv_mix_bwd_w2_kernel, (h->K + 127) / 128, (d.Co + MIX_WT - 1) / MIX_WT, (d.Ci + MIX_WT - 1) / MIX_WT, 128, 0, st,
+                   static_cast<const cplx*>(xhat), gYh, a, dm);
     if ((rc = check_launch(h, 0, "mix_bwd_w"))) return rc;
   }
   if (grad_x) {
-    const int gx = (h->K + 127) / 128, gy = (d.Ci + MIX_OT - 1) / MIX_OT, bt = (batch + MIX_BT - 1) / MIX_BT;
-    int gz = 1184 / (gx * gy);
-    gz = gz < 1 ? 1 : (gz > bt ? bt : gz);
-    TCFD_LAUNCH3(sconv_mix_bwd_x_kernel, gx, gy, gz, 128, 0, st, gYh, gXh, a, dm);
+    if ((rc = launch_mix2<true>(h, gYh, gXh, a, dm, batch, st))) return rc;
     if ((rc = check_launch(h, 0, "mix_bwd_x"))) return rc;
     dm = dims_of(h, d.T_out, d.T_in, batch * d.Ci);
     rc = check_launch(h, xaxis(d.X, false, gXh, Z, static_cast<const cplx*>(h->twx), dm, ncol, batch * d.Ci, st), "xaxis_inv(bwd)");

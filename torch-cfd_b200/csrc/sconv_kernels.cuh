@@ -300,9 +300,12 @@ struct Planes2Smem {
   TCFD_HD static size_t tile_bytes(int T) { return a16((size_t)Y * T * 4); }
   TCFD_HD static size_t zin_bytes(int my, int mt) { return a16((size_t)2 * my * mt * 8); }
   // group: tile | exchange | E/Dh | Xy/D | zin (inverse only) | barrier
+  // (forward: the E entries live in the exchange buffer, which is idle between two transforms -- C4: 18.1 KB per group,
+  // six CTAs of two groups per SM instead of five)
   TCFD_HD static size_t group_bytes(int T, int my, int mt, bool inv) {
-    size_t b = tile_bytes(T) + (size_t)Y * 16 + (size_t)(2 * my + 1) * 16 + (size_t)(2 * my) * xs(T) * 8;
-    if (inv) b += zin_bytes(my, mt);
+    size_t b = tile_bytes(T) + (size_t)Y * 16 + (size_t)(2 * my) * xs(T) * 8;
+    if (inv) b += (size_t)(2 * my + 1) * 16 + zin_bytes(my, mt);
+    else b += 16;  // my = Y/2 keeps Y + 1 entries
     return a16(b + 16);
   }
   TCFD_HD static size_t table_bytes(int T, int mt) {  // [mt][ts(T)] (analysis) or [T][ts(mt)] (synthesis)
@@ -325,8 +328,8 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
   const size_t TB = S::tile_bytes(T);
   const float* tile = reinterpret_cast<const float*>(base);
   cx<f2>* buf = reinterpret_cast<cx<f2>*>(base + TB);
-  cx<f2>* Es = buf + Y;
-  cx<float>* Xy = reinterpret_cast<cx<float>*>(Es + (2 * my + 1));  // [NKY][XS]
+  cx<f2>* Es = buf;  // kept ky of the transform just finished: every thread has left the last exchange (its closing barrier)
+  cx<float>* Xy = reinterpret_cast<cx<float>*>(buf + Y + 1);  // [NKY][XS]
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(Xy) + S::a16((size_t)NKY * XS * 8));
   FftTwiddles<float, Y> tw;
   tw.load(twtab, t);
@@ -577,26 +580,35 @@ struct Planes3Smem {
   TCFD_HD static size_t table_bytes(int T, int mt) { return a16((size_t)T * ts(mt) * 8); }
 };
 
-// U[b] += sum over the kept frequencies; Dh: entries k = 0..my, then k = -my..-1 (the layout of the Hermitian step)
-template <int MYT>
-TCFD_D void pruned_inverse_y(const cx<f2>* Dh, int my, const cx<float> (&w)[MYT], cx<f2> (&z)[8]) {
+// Pruned inverse transform of one thread: in(k) for k in [-nneg, npos) are the non-zero inputs (group-uniform
+// addresses: broadcast reads), w[j-1] = e^{+2 pi i j t / N}; z[h] = output t + h N/8.
+template <int MT, class In>
+TCFD_D void pruned_inverse(In in, int npos, int nneg, const cx<float> (&w)[MT], cx<f2> (&z)[8]) {
 #pragma unroll
   for (int b = 1; b < 8; ++b) z[b] = cx<f2>{f2(0.f), f2(0.f)};
-  z[0] = Dh[0];
+  z[0] = in(0);
 #pragma unroll
-  for (int j = 1; j <= MYT; ++j) {
-    if (j > my) break;  // group-uniform
+  for (int j = 1; j <= MT; ++j) {
+    if (j >= npos && j > nneg) break;  // group-uniform
     const int bp = j & 7, bn = (8 - (j & 7)) & 7;  // compile-time after unrolling
-    const cx<f2> xp = Dh[j], xn = Dh[2 * my + 1 - j];
     const cx<float> wj = w[j - 1];
-    // xp * w
-    z[bp].x = fma_rn(xp.y, -wj.y, fma_rn(xp.x, wj.x, z[bp].x));
-    z[bp].y = fma_rn(xp.y, wj.x, fma_rn(xp.x, wj.y, z[bp].y));
-    // xn * conj(w)
-    z[bn].x = fma_rn(xn.y, wj.y, fma_rn(xn.x, wj.x, z[bn].x));
-    z[bn].y = fma_rn(xn.x, -wj.y, fma_rn(xn.y, wj.x, z[bn].y));
+    if (j < npos) {  // in(+j) * w
+      const cx<f2> xp = in(j);
+      z[bp].x = fma_rn(xp.y, -wj.y, fma_rn(xp.x, wj.x, z[bp].x));
+      z[bp].y = fma_rn(xp.y, wj.x, fma_rn(xp.x, wj.y, z[bp].y));
+    }
+    if (j <= nneg) {  // in(-j) * conj(w)
+      const cx<f2> xn = in(-j);
+      z[bn].x = fma_rn(xn.y, wj.y, fma_rn(xn.x, wj.x, z[bn].x));
+      z[bn].y = fma_rn(xn.x, -wj.y, fma_rn(xn.y, wj.x, z[bn].y));
+    }
   }
   radix8<+1>(z);
+}
+// the y-axis instance; Dh: entries k = 0..my, then k = -my..-1 (the layout of the Hermitian step)
+template <int MYT>
+TCFD_D void pruned_inverse_y(const cx<f2>* Dh, int my, const cx<float> (&w)[MYT], cx<f2> (&z)[8]) {
+  pruned_inverse<MYT>([&](int kk) { return Dh[kk >= 0 ? kk : 2 * my + 1 + kk]; }, my + 1, my, w, z);
 }
 
 template <int Y, int MYT>
@@ -812,6 +824,135 @@ sconv_xaxis_kernel(const cx<float>* __restrict__ in, cx<float>* __restrict__ out
 }
 
 // ------------------------------------------------------------------------------------------
+// Second-generation x-axis kernels: persistent CTAs (twiddles and tables are loaded once), the next [X][GP] tile is in
+// flight (LDGSTS into the other tile buffer) while the current one is transformed.
+//   fwd2: the tile just consumed doubles as the exchange buffer of its transforms (no separate buffers);
+//   inv2: the 2 mx kept inputs of a column pair are broadcast-read by every thread of its group and the transform is the
+//         pruned one (pruned_inverse, no exchanges); the output tile is written back in 128-byte rows.
+template <int X>
+struct Xaxis2Smem {
+  static constexpr int NT = X / 8;
+  static constexpr int GP = (256 / NT) > 8 ? 8 : ((256 / NT) > 0 ? (256 / NT) : 1);
+  static constexpr int RS = GP + 1;  // padded tile row (16-byte entries)
+  static constexpr size_t TILE = (size_t)X * RS * 16;
+  static constexpr size_t FWD_BYTES = 2 * TILE;
+  TCFD_HD static size_t kin_bytes(int mx) { return (size_t)2 * mx * GP * 16; }
+  TCFD_HD static size_t inv_bytes(int mx) { return TILE + 2 * kin_bytes(mx); }
+};
+
+template <int X>
+__global__ void __launch_bounds__(Xaxis2Smem<X>::GP * (X / 8), 3)
+sconv_xaxis_fwd2_kernel(const cx<float>* __restrict__ in, cx<float>* __restrict__ out, const cx<float>* __restrict__ twtab,
+                        SconvDims d, int ncol, int ntx, int ntiles) {
+  typedef Xaxis2Smem<X> S;
+  constexpr int NT = S::NT, GP = S::GP, RS = S::RS;
+  const int mx = d.mx, NKX = 2 * mx;
+  TCFD_DYN_SMEM(smem_raw);
+  const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+  FftTwiddles<float, X> tw;
+  tw.load(twtab, t);
+  GroupSync<NT> sync{1 + g};
+  int parity = 0;
+  const int npairs = ncol / 2;  // ncol is even (2 my mt)
+  // raw tile entry = the two adjacent columns of a pair as they lie in memory: (a.re, a.im, b.re, b.im)
+  auto issue = [&](int tile_id, unsigned char* dstb) {
+    const int pair0 = (tile_id % ntx) * GP;
+    const cx<float>* src = in + (size_t)(tile_id / ntx) * X * ncol;
+    for (int i = threadIdx.x; i < X * GP; i += GP * NT) {
+      const int row = i / GP, gg = i % GP, pr = pair0 + gg;
+      unsigned char* dst = dstb + ((size_t)row * RS + gg) * 16;
+      if (pr < npairs) ldgsts16(dst, src + (size_t)row * ncol + 2 * pr);
+      else *reinterpret_cast<cx<f2>*>(dst) = cx<f2>{f2(0.f), f2(0.f)};
+    }
+    ldgsts_commit();
+  };
+  int cur = 0;
+  if ((int)blockIdx.x < ntiles) issue(blockIdx.x, smem_raw);
+  for (int tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    unsigned char* tb = smem_raw + (size_t)cur * S::TILE;
+    ldgsts_wait_all();
+    __syncthreads();  // the tile is complete; the other buffer (exchange buffer of the previous tile) is free
+    const cx<f2>* tile = reinterpret_cast<const cx<f2>*>(tb);
+    cx<f2> z[1][8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const cx<f2> r = tile[(t + m * NT) * RS + g];  // (a.re, a.im), (b.re, b.im)
+      z[0][m] = cx<f2>{f2(r.x.lo, r.y.lo), f2(r.x.hi, r.y.hi)};
+    }
+    __syncthreads();  // every group holds its column: the tile becomes the exchange buffer
+    const int nxt = tile_id + gridDim.x;
+    if (nxt < ntiles) issue(nxt, smem_raw + (size_t)(cur ^ 1) * S::TILE);
+    fft_run<f2, X, -1, 1, false, X>(z, tw, reinterpret_cast<cx<f2>*>(tb) + (size_t)g * X, parity, t, sync);
+    const int pair = (tile_id % ntx) * GP + g;
+    if (pair < npairs) {
+      cx<float>* dst = out + (size_t)(tile_id / ntx) * NKX * ncol + 2 * pair;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int kxi = kept_index(t + m * NT, X, mx);
+        if (kxi >= 0)  // both columns of the pair in one 16-byte store
+          *reinterpret_cast<cx<f2>*>(dst + (size_t)kxi * ncol) = cx<f2>{f2(z[0][m].x.lo, z[0][m].y.lo), f2(z[0][m].x.hi, z[0][m].y.hi)};
+      }
+    }
+    cur ^= 1;
+  }
+}
+
+template <int X, int MXT>
+__global__ void __launch_bounds__(Xaxis2Smem<X>::GP * (X / 8))
+sconv_xaxis_inv2_kernel(const cx<float>* __restrict__ in, cx<float>* __restrict__ out, const cx<float>* __restrict__ twtab,
+                        SconvDims d, int ncol, int ntx, int ntiles) {
+  typedef Xaxis2Smem<X> S;
+  constexpr int NT = S::NT, GP = S::GP, RS = S::RS;
+  const int mx = d.mx, NKX = 2 * mx;
+  TCFD_DYN_SMEM(smem_raw);
+  cx<f2>* tile = reinterpret_cast<cx<f2>*>(smem_raw);  // [X][RS], raw pairs
+  unsigned char* kin0 = smem_raw + S::TILE;
+  const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+  cx<float> w[MXT];
+#pragma unroll
+  for (int j = 1; j <= MXT; ++j) w[j - 1] = conj(twtab[(j * t) & (X - 1)]);
+  const int npairs = ncol / 2;
+  auto issue = [&](int tile_id, unsigned char* dstb) {  // the kept rows of the tile's GP column pairs: [NKX][GP] raw pairs
+    const int pair0 = (tile_id % ntx) * GP;
+    const cx<float>* src = in + (size_t)(tile_id / ntx) * NKX * ncol;
+    for (int i = threadIdx.x; i < NKX * GP; i += GP * NT) {
+      const int row = i / GP, gg = i % GP, pr = pair0 + gg;
+      unsigned char* dst = dstb + (size_t)i * 16;
+      if (pr < npairs) ldgsts16(dst, src + (size_t)row * ncol + 2 * pr);
+      else *reinterpret_cast<cx<f2>*>(dst) = cx<f2>{f2(0.f), f2(0.f)};
+    }
+    ldgsts_commit();
+  };
+  int cur = 0;
+  if ((int)blockIdx.x < ntiles) issue(blockIdx.x, kin0);
+  for (int tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    const cx<f2>* kin = reinterpret_cast<const cx<f2>*>(kin0 + (size_t)cur * S::kin_bytes(mx));
+    ldgsts_wait_all();
+    __syncthreads();  // inputs complete; the previous tile has been written out, the other input buffer is free
+    const int nxt = tile_id + gridDim.x;
+    if (nxt < ntiles) issue(nxt, kin0 + (size_t)(cur ^ 1) * S::kin_bytes(mx));
+    cx<f2> z[8];
+    pruned_inverse<MXT>(
+        [&](int kk) {
+          const cx<f2> r = kin[(kk >= 0 ? kk : NKX + kk) * GP + g];
+          return cx<f2>{f2(r.x.lo, r.y.lo), f2(r.x.hi, r.y.hi)};
+        },
+        mx, mx, w, z);
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+      tile[(t + m * NT) * RS + g] = cx<f2>{f2(z[m].x.lo, z[m].y.lo), f2(z[m].x.hi, z[m].y.hi)};  // back to raw pairs
+    __syncthreads();
+    const int pair0 = (tile_id % ntx) * GP;
+    cx<float>* dst = out + (size_t)(tile_id / ntx) * X * ncol;
+    for (int i = threadIdx.x; i < X * GP; i += GP * NT) {
+      const int row = i / GP, gg = i % GP, pr = pair0 + gg;
+      if (pr < npairs) *reinterpret_cast<cx<f2>*>(dst + (size_t)row * ncol + 2 * pr) = tile[row * RS + gg];
+    }
+    cur ^= 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // mode mixing.  Modes are indexed k = (kxi * NKY + kyi) * mt + kt; corner = (kxi >= mx) + 2 (kyi >= my);
 // weights of a corner: [Ci][Co][mx][my][mt] complex (the reference's parameter layout).
 struct MixArgs {
@@ -936,6 +1077,120 @@ sconv_mix_bwd_w_kernel(const cx<float>* __restrict__ Xh, const cx<float>* __rest
   }
   a.gw[corner][((size_t)i * a.Co + o) * msz + widx] = acc;
   if (i == 0 && o == 0 && a.gbias[corner]) {
+    cx<float> s{0.f, 0.f};
+    for (int b = 0; b < a.B; ++b)
+      for (int oo = 0; oo < a.Co; ++oo) s = s + gYh[((size_t)b * a.Co + oo) * K + k];
+    a.gbias[corner][widx] = cx<float>{a.delta * s.x, a.delta * s.y};
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Second-generation mode mixing.  The first-generation kernels above re-read every Xh entry once per output-channel
+// tile and every weight once per batch tile through L2 (C4: 0.5 GB of L2 traffic for 0.17 GB of data, 12 warps per
+// SM at 160 registers) and, in the weight gradient, every entry Ci (or Co) times (2.6 GB).  Here
+//   mix2<BWD>   CTA = 32 consecutive modes x one warp per tile of MIX_OT output channels; the batch tile of the INPUT
+//               spectrum (MIX_BT x P channels x 32 modes) is staged in shared memory once and shared by all warps;
+//               BWD = false:  Yh[b][o] = sum_i Xh[b][i] W[i][o] (+ delta bias);   BWD = true:  gXh[b][i] = sum_o gYh[b][o] conj(W[i][o])
+//   mix_bwd_w2  thread = (mode, tile of 4 i, tile of 4 o): 8 loads per 16 multiply-adds instead of 2 per 1.
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+sconv_mix2_kernel(const cx<float>* __restrict__ in, cx<float>* __restrict__ out, MixArgs a, SconvDims d) {
+  const int K = 4 * d.mx * d.my * d.mt, msz = d.mx * d.my * d.mt;
+  const int P = BWD ? a.Co : a.Ci, Q = BWD ? a.Ci : a.Co;  // input / output channels of this product
+  TCFD_DYN_SMEM(smem_raw);
+  cx<float>* xs = reinterpret_cast<cx<float>*>(smem_raw);  // [MIX_BT][P][32]
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5, q0 = wq * MIX_OT;
+  const int k = blockIdx.x * 32 + lane;
+  const bool kv = k < K;
+  const int kc = kv ? k : K - 1;
+  int corner, widx;
+  mode_split(kc, d, corner, widx);
+  const cx<float>* w = a.w[corner] + widx;
+  cx<float> bias{0.f, 0.f};
+  if (!BWD && a.bias[corner]) {
+    const cx<float> bb = a.bias[corner][widx];
+    bias = cx<float>{a.delta * bb.x, a.delta * bb.y};
+  }
+  for (int b0 = (int)blockIdx.y * MIX_BT; b0 < a.B; b0 += (int)gridDim.y * MIX_BT) {
+    // stage the input tile: rows of 32 consecutive modes (256 contiguous bytes) as 16-byte asynchronous copies, all
+    // in flight at once (K is even and the tile starts at a multiple of 32 modes: pairs never straddle the end)
+    for (int e = threadIdx.x; e < MIX_BT * P * 16; e += blockDim.x) {
+      const int l2 = e & 15, r = e >> 4, p = r % P, j = r / P;
+      const int kk = blockIdx.x * 32 + 2 * l2;
+      cx<float>* dst = xs + (size_t)r * 32 + 2 * l2;
+      if (b0 + j < a.B && kk < K) ldgsts16(dst, in + ((size_t)(b0 + j) * P + p) * K + kk);
+      else dst[0] = dst[1] = cx<float>{0.f, 0.f};
+    }
+    ldgsts_commit();
+    ldgsts_wait_all();
+    __syncthreads();
+    if (q0 < Q) {
+      cx<float> acc[MIX_BT][MIX_OT];
+#pragma unroll
+      for (int j = 0; j < MIX_BT; ++j)
+#pragma unroll
+        for (int q = 0; q < MIX_OT; ++q) acc[j][q] = cx<float>{0.f, 0.f};
+#pragma unroll 2
+      for (int p = 0; p < P; ++p) {
+        cx<float> wv[MIX_OT], xv[MIX_BT];
+#pragma unroll
+        for (int q = 0; q < MIX_OT; ++q) {
+          const int qq = q0 + q < Q ? q0 + q : Q - 1;
+          wv[q] = BWD ? w[((size_t)qq * a.Co + p) * msz] : w[((size_t)p * a.Co + qq) * msz];
+        }
+#pragma unroll
+        for (int j = 0; j < MIX_BT; ++j) xv[j] = xs[(j * P + p) * 32 + lane];
+#pragma unroll
+        for (int j = 0; j < MIX_BT; ++j)
+#pragma unroll
+          for (int q = 0; q < MIX_OT; ++q) acc[j][q] = acc[j][q] + (BWD ? cmul_conj(xv[j], wv[q]) : cmul(xv[j], wv[q]));
+      }
+      if (kv) {
+#pragma unroll
+        for (int j = 0; j < MIX_BT; ++j)
+#pragma unroll
+          for (int q = 0; q < MIX_OT; ++q)
+            if (b0 + j < a.B && q0 + q < Q) out[((size_t)(b0 + j) * Q + q0 + q) * K + k] = acc[j][q] + bias;
+      }
+    }
+    __syncthreads();  // the tile is re-used by the next batch tile
+  }
+}
+
+constexpr int MIX_WT = 4;  // channel tile (both i and o) of the weight-gradient kernel
+
+// gW[i][o][k] = sum_b conj(Xh[b][i][k]) gYh[b][o][k]; thread = (k, tile of MIX_WT o, tile of MIX_WT i)
+// gbias[k] = delta * sum_{b,o} gYh[b][o][k]  (computed by the threads of the first tiles)
+__global__ void __launch_bounds__(128)
+sconv_mix_bwd_w2_kernel(const cx<float>* __restrict__ Xh, const cx<float>* __restrict__ gYh, MixArgs a, SconvDims d) {
+  const int K = 4 * d.mx * d.my * d.mt, msz = d.mx * d.my * d.mt;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, o0 = blockIdx.y * MIX_WT, i0 = blockIdx.z * MIX_WT;
+  if (k >= K) return;
+  int corner, widx;
+  mode_split(k, d, corner, widx);
+  cx<float> acc[MIX_WT][MIX_WT];
+#pragma unroll
+  for (int i = 0; i < MIX_WT; ++i)
+#pragma unroll
+    for (int o = 0; o < MIX_WT; ++o) acc[i][o] = cx<float>{0.f, 0.f};
+#pragma unroll 2
+  for (int b = 0; b < a.B; ++b) {
+    cx<float> xv[MIX_WT], gv[MIX_WT];
+#pragma unroll
+    for (int i = 0; i < MIX_WT; ++i) xv[i] = Xh[((size_t)b * a.Ci + (i0 + i < a.Ci ? i0 + i : a.Ci - 1)) * K + k];
+#pragma unroll
+    for (int o = 0; o < MIX_WT; ++o) gv[o] = gYh[((size_t)b * a.Co + (o0 + o < a.Co ? o0 + o : a.Co - 1)) * K + k];
+#pragma unroll
+    for (int i = 0; i < MIX_WT; ++i)
+#pragma unroll
+      for (int o = 0; o < MIX_WT; ++o) acc[i][o] = acc[i][o] + cmul_conj(gv[o], xv[i]);  // g * conj(x)
+  }
+#pragma unroll
+  for (int i = 0; i < MIX_WT; ++i)
+#pragma unroll
+    for (int o = 0; o < MIX_WT; ++o)
+      if (i0 + i < a.Ci && o0 + o < a.Co) a.gw[corner][((size_t)(i0 + i) * a.Co + o0 + o) * msz + widx] = acc[i][o];
+  if (i0 == 0 && o0 == 0 && a.gbias[corner]) {
     cx<float> s{0.f, 0.f};
     for (int b = 0; b < a.B; ++b)
       for (int oo = 0; oo < a.Co; ++oo) s = s + gYh[((size_t)b * a.Co + oo) * K + k];
