@@ -56,6 +56,19 @@ def test_emu_sconv_vs_reference_golden(tag, kind, cfg):
     ((1, 1, 32, 64, 5), (3, 12, 3), dict()),                                      # ... my in (8, 16], odd mt (one copy)
 ])
 def test_emu_sconv_vs_oracle(shape, modes, kw):
+    _sconv_vs_oracle(shape, modes, kw)
+
+
+@pytest.mark.parametrize("env", [{"TCFD_SCONV_PLANES": "2"}, {"TCFD_SCONV_PLANES": "1"}, {"TCFD_SCONV_XAXIS": "1"},
+                                 {"TCFD_SCONV_MIX": "1"}, {"TCFD_SCONV_MIX": "2"}])
+def test_emu_sconv_kernel_generations(env, monkeypatch):
+    """Every kernel generation the library still carries (the switches are read at each call) meets the same bar."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _sconv_vs_oracle((2, 3, 32, 64, 6), (5, 7, 4), dict(bias=True, delta=0.5))
+
+
+def _sconv_vs_oracle(shape, modes, kw):
     torch.manual_seed(3)
     b, Ci, X, Y, T = shape
     Co, (mx, my, mt) = 2, modes

@@ -62,6 +62,20 @@ def test_modules_vs_reference_golden(tag, kind, cfg):
 @pytest.mark.parametrize("X,Y,T,modes", [(64, 128, 10, (12, 20, 6)), (256, 64, 16, (20, 8, 8)), (128, 128, 7, (8, 8, 4)),
                                             (64, 256, 10, (6, 28, 6)), (32, 64, 6, (4, 12, 4)), (32, 512, 4, (4, 20, 3))])
 def test_modules_vs_oracle_sizes(X, Y, T, modes):
+    _modules_vs_oracle(X, Y, T, modes)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"TCFD_SCONV_PLANES": "2"}, {"TCFD_SCONV_PLANES": "1"}, {"TCFD_SCONV_XAXIS": "1"},
+                                 {"TCFD_SCONV_MIX": "1"}, {"TCFD_SCONV_MIX": "2"}])
+def test_kernel_generations_vs_oracle(env, monkeypatch):
+    """The older kernel generations kept as fall-backs (odd sizes, unaligned views) and A/B switches: same parity bar."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _modules_vs_oracle(64, 128, 10, (12, 20, 6))
+
+
+def _modules_vs_oracle(X, Y, T, modes):
     from torch_cfd_b200.fno import SpectralConvS
     torch.manual_seed(5)
     mx, my, mt = modes

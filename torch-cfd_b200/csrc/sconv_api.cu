@@ -112,13 +112,9 @@ int planes_grid(const void* kernel, int threads, size_t smem, int want) {
 #endif
 }
 // TCFD_SCONV_PLANES = 1 / 2: force the first / second generation plane kernels (bring-up and A/B timing)
-int planes_gen() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TCFD_SCONV_PLANES");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+int planes_gen() {  // read at every call: tests switch generations inside one process
+  const char* e = getenv("TCFD_SCONV_PLANES");
+  return e ? atoi(e) : 0;
 }
 bool planes_v1() { return planes_gen() == 1; }
 template <int Y>
@@ -176,13 +172,9 @@ int launch_xaxis(const cplx* in, cplx* out, const cplx* tw, SconvDims d, int nco
 }
 
 // second-generation x-axis kernels (persistent, prefetching); TCFD_SCONV_XAXIS = 1 forces the first generation
-int xaxis_gen() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TCFD_SCONV_XAXIS");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+int xaxis_gen() {  // read at every call: tests switch generations inside one process
+  const char* e = getenv("TCFD_SCONV_XAXIS");
+  return e ? atoi(e) : 0;
 }
 template <int X>
 int launch_xaxis_fwd2(const cplx* in, cplx* out, const cplx* tw, SconvDims d, int ncol, int nslabs, cudaStream_t st) {
@@ -338,13 +330,9 @@ extern "C" int tcfd_sconv3d_last_launch_count(const tcfd_sconv3d_t* h) { return 
 
 namespace {
 // TCFD_SCONV_MIX = 1: first-generation mode-mixing kernels everywhere, 2: second generation everywhere (A/B timing)
-int mix_gen() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TCFD_SCONV_MIX");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+int mix_gen() {  // read at every call: tests switch generations inside one process
+  const char* e = getenv("TCFD_SCONV_MIX");
+  return e ? atoi(e) : 0;
 }
 // Yh = Xh x W (BWD = false) or gXh = gYh x conj(W)^T (BWD = true)
 template <bool BWD>
