@@ -1130,7 +1130,7 @@ sconv_mix2_kernel(const cx<float>* __restrict__ in, cx<float>* __restrict__ out,
       for (int j = 0; j < MIX_BT; ++j)
 #pragma unroll
         for (int q = 0; q < MIX_OT; ++q) acc[j][q] = cx<float>{0.f, 0.f};
-#pragma unroll 2
+#pragma unroll 4
       for (int p = 0; p < P; ++p) {
         cx<float> wv[MIX_OT], xv[MIX_BT];
 #pragma unroll
