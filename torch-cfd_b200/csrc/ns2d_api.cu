@@ -211,6 +211,7 @@ int make_tile_maps(tcfd_ns2d* h) {
   h->maps.base = static_cast<const unsigned char*>(h->H);
   h->maps.row_bytes = row_bytes;
   h->maps.sample_bytes = row_bytes * h->n;
+  h->maps.adv_base = static_cast<const unsigned char*>(h->advt);
   return 0;
 #else
   void* fn = nullptr;
@@ -228,6 +229,17 @@ int make_tile_maps(tcfd_ns2d* h) {
   CUresult r = encode(&h->maps.main, dt, 3, h->H, gdim, gstr, box_main, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TCFD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  if (h->flow) {
+    // advection rows of the dataflow schedule: [chunk][JB blocks][N columns][8 rows][4 reals] (tma.cuh)
+    const cuuint64_t jb = (cuuint64_t)((h->n / 4 + 1 + tcfd::ADV_BLOCK - 1) / tcfd::ADV_BLOCK);
+    const cuuint64_t adim[4] = {4, (cuuint64_t)tcfd::ADV_BLOCK, (cuuint64_t)h->n, (cuuint64_t)h->chunk * jb};
+    const cuuint64_t astr[3] = {(cuuint64_t)ent, (cuuint64_t)ent * tcfd::ADV_BLOCK, (cuuint64_t)ent * tcfd::ADV_BLOCK * h->n};
+    const cuuint32_t aest[4] = {1, 1, 1, 1};
+    const cuuint32_t abox[4] = {4, 1, rows, 1};
+    r = encode(&h->maps.adv, dt, 4, h->advt, adim, astr, abox, aest, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TCFD_ERR_CUDA, "cuTensorMapEncodeTiled (advection rows) failed with CUresult " + std::to_string((int)r));
+  }
   return 0;
 #endif
 }
@@ -515,7 +527,9 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
     h->chunk = chunk;
     const size_t sb = h->state_bytes(h->chunk);
     // advt: v1 [B][nh][n] complex; v2 [B][n/4+1][n][4 reals] (slightly larger)
-    const size_t ab = (size_t)h->chunk * (h->n / 4 + 1) * h->n * 4 * h->es;
+    // (dataflow schedule: rows padded to whole blocks of ADV_BLOCK, tma.cuh)
+    const size_t adv_rows = h->flow ? (size_t)((h->n / 4 + 1 + tcfd::ADV_BLOCK - 1) / tcfd::ADV_BLOCK) * tcfd::ADV_BLOCK : (size_t)(h->n / 4 + 1);
+    const size_t ab = (size_t)h->chunk * adv_rows * h->n * 4 * h->es;
     // unit-layout state (v2): [B][n/4+1][2][nh] entries of 4 reals
     const size_t ub = (size_t)h->chunk * (h->n / 4 + 1) * 2 * h->nh * 4 * h->es;
     // H: first generation [B][nh][n/yt][4][yt] = 4 * nh * n complex per sample; second generation

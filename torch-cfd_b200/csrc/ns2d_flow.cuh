@@ -160,8 +160,8 @@ struct FlowSmem {
   static constexpr int TABM = R::TAB_BYTES + 2 * R::MASK_ROW;  // one table block + its mask rows
   static constexpr int OFF_W = 0;
   static constexpr int OFF_H = R::UNIT_BYTES;
-  static constexpr int OFF_ADV = 2 * R::UNIT_BYTES;  // UNIT_BYTES >= N entries
-  static constexpr int OFF_TAB = 3 * R::UNIT_BYTES;
+  static constexpr int OFF_ADV = (2 * R::UNIT_BYTES + 127) / 128 * 128;  // UNIT_BYTES >= N entries; tiled TMA destination: 128 B aligned
+  static constexpr int OFF_TAB = (OFF_ADV + R::UNIT_BYTES + 15) / 16 * 16;
   static constexpr int ROWS_STAGE = OFF_TAB + 2 * TABM;
   static constexpr int AREA = (G::BYTES > ROWS_STAGE ? G::BYTES : ROWS_STAGE);
   static constexpr int OFF_BUF = (AREA + 127) / 128 * 128;
@@ -230,6 +230,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
   typedef typename S::G G;
   typedef typename S::R R;
   constexpr int NT = N / 8, NH = N / 2 + 1, ND = N / 4 + 1, NQ = N / 4;
+  constexpr int JB = (ND + ADV_BLOCK - 1) / ADV_BLOCK;  // blocks of advection rows per slot
   constexpr int IR = (ND + GR - 1) / GR;  // rows items per sample and phase
   constexpr int IC = NQ / GC;             // cols items per sample and phase
   static_assert(NQ % GC == 0, "GC must divide N/4");
@@ -282,6 +283,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
     stage_barrier_init(bar_o);
 #ifndef TCFD_EMU
     tma_prefetch_desc(&maps.main);
+    tma_prefetch_desc(&maps.adv);
 #endif
     next_tk = flow_fetch_add(ticket, 1);
     sh[0] = next_tk;
@@ -346,8 +348,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         if (rd_h_) bulk_load(area + S::OFF_H, fp.hU + ub_, (unsigned)R::UNIT_BYTES, bar_s);
         if (d < p.NDF) {
           stage_expect(bar_a, (unsigned)(N * sizeof(cx<L>)));
-          bulk_load(area + S::OFF_ADV, reinterpret_cast<const cx<L>*>(p.advt2) + ((size_t)sl_ * ND + d) * N,
-                    (unsigned)(N * sizeof(cx<L>)), bar_a);
+          adv_row_issue<N, (int)sizeof(cx<L>)>(area + S::OFF_ADV, maps, d % ADV_BLOCK, sl_ * JB + d / ADV_BLOCK, bar_a);
         }
       }
     };
@@ -424,18 +425,19 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
 #pragma unroll
         for (int m = 0; m < 8; ++m) sbuf[t + m * NT] = cc[0][m];
         __syncthreads();
-        cx<L>* dst = reinterpret_cast<cx<L>*>(p.advt2) + (size_t)sl * ND * N + y0;
+        // blocked layout [slot][jj / 8][y][jj % 8] (tma.cuh): eight consecutive lanes write one 128-byte line
+        cx<L>* dst = reinterpret_cast<cx<L>*>(p.advt2) + ((size_t)sl * JB * N + y0) * ADV_BLOCK;
         for (int jj = t; jj < p.NDF; jj += NT) {
           const int k = 2 * jj;
           const cx<L> c0 = sbuf[k], c1 = sbuf[k + 1], n0 = sbuf[(N - k) % N], n1 = sbuf[N - k - 1];
           const L hf(T(0.5));
           const L Ea = hf * (c0.x + n0.x), Fa = hf * (c0.y - n0.y), Ga = hf * (c0.y + n0.y), Ha = hf * (n0.x - c0.x);
           const L Eb = hf * (c1.x + n1.x), Fb = hf * (c1.y - n1.y), Gb = hf * (c1.y + n1.y), Hb = hf * (n1.x - c1.x);
-          cx<L>* o = dst + (size_t)jj * N;
-          o[0] = cx<L>{L(Ea.lo, Eb.lo), L(Fa.lo, Fb.lo)};
-          o[1] = cx<L>{L(Ga.lo, Gb.lo), L(Ha.lo, Hb.lo)};
-          o[2] = cx<L>{L(Ea.hi, Eb.hi), L(Fa.hi, Fb.hi)};
-          o[3] = cx<L>{L(Ga.hi, Gb.hi), L(Ha.hi, Hb.hi)};
+          cx<L>* o = dst + (size_t)(jj / ADV_BLOCK) * N * ADV_BLOCK + (jj % ADV_BLOCK);
+          o[0 * ADV_BLOCK] = cx<L>{L(Ea.lo, Eb.lo), L(Fa.lo, Fb.lo)};
+          o[1 * ADV_BLOCK] = cx<L>{L(Ga.lo, Gb.lo), L(Ha.lo, Hb.lo)};
+          o[2 * ADV_BLOCK] = cx<L>{L(Ea.hi, Eb.hi), L(Fa.hi, Fb.hi)};
+          o[3 * ADV_BLOCK] = cx<L>{L(Ga.hi, Gb.hi), L(Ha.hi, Hb.hi)};
         }
         if (g + 1 < GC && !PP) __syncthreads();  // buf is re-used by the next quad's transforms
       }

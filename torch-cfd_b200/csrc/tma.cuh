@@ -16,16 +16,23 @@ namespace tcfd {
 // inverse transform of column y (rows kx > N/2 are written by the rows units as conjugates, so the column
 // kernel reads every entry once and does no Hermitian unpacking).  A tile is, for every row kx of one
 // sample, the 4 entries of 4 consecutive columns y.
+// The advection rows of the dataflow schedule (ns2d_flow.cuh) live in blocks of 8 rows, [slot][row / 8][y][row % 8]
+// entries: a cols item writes, for each of its 4 columns y, the entries of ALL rows -- with 8 consecutive rows adjacent
+// a warp's store covers 4 cache lines instead of 29 (ncu: these stores were 43 % of the kernel's global-memory tag
+// requests) -- and a rows unit pulls its row (N entries, one per 8-entry line) with a rank-4 tiled copy (`adv`).
 #ifndef TCFD_EMU
 struct alignas(64) TileMaps {
   CUtensorMap main;  // rank 3, box {4 entries, min(256, N) rows, 1 sample}
+  CUtensorMap adv;   // rank 4 {4 reals, 8 rows of a block, N columns y, slots x blocks}, box {4, 1, min(256, N), 1}
 };
 #else
 struct TileMaps {
   const unsigned char* base;
   size_t row_bytes, sample_bytes;
+  const unsigned char* adv_base;
 };
 #endif
+constexpr int ADV_BLOCK = 8;
 
 // Shared-memory image of a tile with NR rows whose inner box is IB = 64 or 128 bytes (hardware swizzle of
 // the same width).  The rows arrive in boxes of BOX rows, stored [box][row][IB] (i.e. row-major).
@@ -191,6 +198,21 @@ TCFD_D void tile_load_issue(unsigned char* tile, const TileMaps& maps, int y0, i
     const unsigned char* src = maps.base + (size_t)sample * maps.sample_bytes + (size_t)r * maps.row_bytes + (size_t)y0 * ent;
     for (int j = 0; j < IB / 16; ++j) std::memcpy(tile + G::chunk_offset(r, j), src + 16 * j, 16);
   }
+#endif
+}
+
+// Issue the load of advection row `row` of block-row index `blk` (= slot * blocks_per_slot + row / 8): NR entries of ENT
+// bytes into dst (called by ONE thread, after stage_expect on the same barrier).
+template <int NR, int ENT>
+TCFD_D void adv_row_issue(unsigned char* dst, const TileMaps& maps, int row_in_block, int blk, unsigned long long* bar) {
+  constexpr int BOX = NR < 256 ? NR : 256;
+#ifndef TCFD_EMU
+#pragma unroll
+  for (int b = 0; b < NR / BOX; ++b) tma_load_4d(dst + (size_t)b * BOX * ENT, &maps.adv, 0, row_in_block, b * BOX, blk, bar);
+#else
+  (void)bar;
+  const unsigned char* src = maps.adv_base + ((size_t)blk * NR * ADV_BLOCK + row_in_block) * ENT;
+  for (int y = 0; y < NR; ++y) std::memcpy(dst + (size_t)y * ENT, src + (size_t)y * ADV_BLOCK * ENT, ENT);
 #endif
 }
 
