@@ -395,8 +395,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
         cx<L> cc[1][8];
         FLOW_LOADWAIT(bar_s, phase_s);
         phase_s ^= 1u;
-#pragma unroll
-        for (int cidx = 0; cidx < 4; ++cidx) {
+        auto column = [&](int cidx) {
           cx<L> z[1][8];
 #pragma unroll
           for (int m = 0; m < 8; ++m) z[0][m] = tile_ld<T, G>(tile, t + m * NT, cidx);
@@ -416,6 +415,13 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
             if (cidx == 2) cc[0][m].x.hi = adv;
             if (cidx == 3) cc[0][m].y.hi = adv;
           }
+        };
+        if constexpr ((MODE & 8) != 0) {  // experiment: one copy of the column body (instruction-cache footprint)
+#pragma unroll 1
+          for (int cidx = 0; cidx < 4; ++cidx) column(cidx);
+        } else {
+#pragma unroll
+          for (int cidx = 0; cidx < 4; ++cidx) column(cidx);
         }
         FLOW_FFT(-1, cc);
         // separation buffer: with ping-pong exchanges it is the half the next exchange would write (the other

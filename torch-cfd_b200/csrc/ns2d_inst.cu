@@ -263,6 +263,8 @@ int launch_flow(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms,
   TCFD_FLOW_CASE(1, 1, 5)
   TCFD_FLOW_CASE(3, 4, 5)
   TCFD_FLOW_CASE(2, 2, 5)
+  // rolled column loop of the cols items
+  if (gr == 3 && gc == 4 && mr == 8) return launch_flow_g<3, 4, MR, 8>(fp, maps, num_sms, stream, win);
   // ping-pong exchange buffers
   if (gr == 3 && gc == 4 && mr == 2) return launch_flow_g<3, 4, MR, 2>(fp, maps, num_sms, stream, win);
   if (gr == 1 && gc == 1 && mr == 2) return launch_flow_g<1, 1, MR, 2>(fp, maps, num_sms, stream, win);
