@@ -166,7 +166,11 @@ struct FlowSmem {
   static constexpr int AREA = (G::BYTES > ROWS_STAGE ? G::BYTES : ROWS_STAGE);
   static constexpr int OFF_BUF = (AREA + 127) / 128 * 128;
   static constexpr int OFF_BAR = OFF_BUF + VB * N * (int)sizeof(cx<L>);
-  static constexpr int BYTES = OFF_BAR + 64 + 1024;  // + slack for the 1 KB alignment of the area
+  // per-CTA copies of the small per-row tables every rows unit reads (kappa_x[N], forced-row flags[N]): shared-memory
+  // reads instead of four dependent global loads at the head of every unit (long-scoreboard stalls in the ncu source view)
+  static constexpr int OFF_KX = OFF_BAR + 64;
+  static constexpr int OFF_FR = OFF_KX + N * (int)sizeof(T);
+  static constexpr int BYTES = OFF_FR + (N + 15) / 16 * 16 + 1024;  // + slack for the 1 KB alignment of the area
 };
 
 template <class L>
@@ -261,6 +265,13 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
   T kyv[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) kyv[m] = p.kappa_y[m < 4 ? t + m * NT : N - t - m * NT];
+  const T ky0 = p.kappa_y[0], kyh = p.kappa_y[N / 2];
+  T* kxs = reinterpret_cast<T*>(area + S::OFF_KX);
+  unsigned char* frs = area + S::OFF_FR;
+  for (int i = t; i < N; i += NT) {
+    kxs[i] = p.kappa_x[i];
+    frs[i] = p.fhat ? p.frow[i] : (unsigned char)0;
+  }
 
   int* ticket = fp.sync;
   int* cnt_rows = fp.sync + 2;
@@ -489,7 +500,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
       const int r1a = 2 * d, r2a = (N - r1a) % N;
       const int r1b = valid1 ? 2 * d + 1 : r1a, r2b = (N - r1b) % N;
       const bool selfa = r1a == r2a, selfb = r1b == r2b;
-      const T kx1a = p.kappa_x[r1a], kx2a = p.kappa_x[r2a], kx1b = p.kappa_x[r1b], kx2b = p.kappa_x[r2b];
+      const T kx1a = kxs[r1a], kx2a = kxs[r2a], kx1b = kxs[r1b], kx2b = kxs[r2b];
       const unsigned char* tabsrc = area + S::OFF_TAB + tabsel * S::TABM;
       const L* linst = reinterpret_cast<const L*>(tabsrc);
       const T* nilst = reinterpret_cast<const T*>(tabsrc) + 2 * NH;
@@ -532,7 +543,7 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
           }
         }
       } else {
-        const bool forced = p.fhat && (p.frow[r1a] | p.frow[r2a] | p.frow[r1b] | p.frow[r2b]);
+        const bool forced = (frs[r1a] | frs[r2a] | frs[r1b] | frs[r2b]) != 0;
         cx<L> a[1][8];
         if (d < p.NDF) {
           FLOW_LOADWAIT(bar_a, phase_a);
@@ -630,7 +641,6 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
 
       if (do_inv) {
         FLOW_MARK(6);
-        const T ky0 = p.kappa_y[0], kyh = p.kappa_y[N / 2];
         // per lane (row pair) two transforms: type 0 ("P" = A + i B) gives row r1 of z, type 1 ("Q" = A - i B,
         // stored conjugated) row r2 = N - r1 (ns2d_v2.cuh: ns_fields_z); self-paired rows need P only
         const int nq = valid1 ? 4 : 2;
@@ -656,13 +666,13 @@ ns2d_flow_kernel(const FlowParams<T> fp, const
           }
           if (t == 0 && (MODE & 4) == 0) {
             // self-conjugate columns ky = 0 and ky = N/2: Hermitian part of the two rows (C2R semantics)
+            // (thread 0's generic entries m = 0 and m = 4 above ARE f(w[r1][0]) and conj f(w[r2][N/2]): only the two
+            // partner entries are evaluated here -- this block runs on one lane while the other warp waits)
             const T n0 = nl[0], nh = nl[N / 2];
-            const cx<L> f1 = ns_fields_z<T>(lane_rt(wv[0], lane), n0, kx1, ky0, sg);
             const cx<L> f2_ = ns_fields_z<T>(lane_rt(e0, lane), n0, kx2, ky0, -sg);
             const cx<L> g1 = ns_fields_z<T>(lane_rt(e1, lane), nh, kx1, kyh, sg);
-            const cx<L> g2 = ns_fields_z<T>(lane_rt(wv[4], lane), nh, kx2, kyh, -sg);
-            z[0][0] = L(T(0.5)) * (f1 + conj(f2_));
-            z[0][4] = L(T(0.5)) * (g1 + conj(g2));
+            z[0][0] = L(T(0.5)) * (z[0][0] + conj(f2_));
+            z[0][4] = L(T(0.5)) * (g1 + z[0][4]);
           }
           FLOW_FFT(+1, z);
           cx<L>* Hrow = reinterpret_cast<cx<L>*>(p.H2) + ((size_t)sl * N + row) * (size_t)N + t;
