@@ -260,6 +260,10 @@ int launch_flow(const FlowParams<real_t>& fp, const TileMaps* maps, int num_sms,
   TCFD_FLOW_CASE(1, 1, 0)
   TCFD_FLOW_CASE(3, 4, 0)
   TCFD_FLOW_CASE(2, 2, MR)
+  TCFD_FLOW_CASE(4, 4, MR)
+  TCFD_FLOW_CASE(3, 8, MR)
+  TCFD_FLOW_CASE(2, 4, MR)
+  TCFD_FLOW_CASE(5, 4, MR)
   TCFD_FLOW_CASE(1, 1, 5)
   TCFD_FLOW_CASE(3, 4, 5)
   TCFD_FLOW_CASE(2, 2, 5)
