@@ -560,7 +560,9 @@ extern "C" int tcfd_ns2d_create(tcfd_ns2d_t** out, const tcfd_ns2d_desc_t* d) {
           off += nbs[i];
         }
         // grouped items (3 double rows / 4 quads per ticket) need a wide window to keep every SM busy
-        h->win.grouped = (h->n >= 512 && h->chunk >= 24) ? 1 : 0;
+        // (>= ~1000 grouped rows items per phase: 512^2 from 24 samples, 1024^2 from 12 -- measured 809 vs 734 steps/s at
+        // 1024^2 x 16; at 256^2 the one-warp CTAs prefer single units: 3430 vs 2330 steps/s, profiles/r2o_flow_sweep.jsonl)
+        h->win.grouped = (h->n >= 512 && (long long)h->chunk * ((h->n / 4 + 1 + 2) / 3) >= 1000) ? 1 : 0;
 #ifndef TCFD_EMU
         const size_t hot = total - nbs[5];  // everything but hB (used by the two-launch schedule only)
         int dev = 0, max_persist = 0, max_win = 0;
