@@ -202,6 +202,14 @@ void fill_params(const tcfd_ns2d* h, tcfd::NsParams<T>& p, int batch) {
   p.fhat = static_cast<const tcfd::cx<T>*>(h->fhat);
 }
 
+// bound of a dependency wait of the dataflow kernel in SM cycles (about 2 GHz): TCFD_FLOW_TIMEOUT_S seconds, default 3,
+// 0 = wait for ever (cuda-gdb, compute-sanitizer, time-sliced GPUs)
+long long flow_wait_cycles() {
+  double s = 3.0;
+  if (const char* e = getenv("TCFD_FLOW_TIMEOUT_S")) s = atof(e);
+  return s <= 0.0 ? 0ll : (long long)(s * 2.0e9);
+}
+
 // TMA descriptor over H2 = [chunk][N rows kx][N] packed-complex entries (4 reals each): a tile is 4
 // consecutive entries of every row of one sample.
 int make_tile_maps(tcfd_ns2d* h) {
@@ -359,6 +367,7 @@ int flow_step_impl(tcfd_ns2d* h, const void* w_in, void* w_out, void* dwdt, int 
   fp.hU = static_cast<CU*>(h->hA);
   fp.sync = h->sync_dev;
   fp.err = h->err_dev;
+  fp.wait_cycles = flow_wait_cycles();
   fp.prof = h->prof_dev;
   CUDA_TRY(cudaMemsetAsync(h->sync_dev, 0, sizeof(int) * (2 + 2 * (size_t)h->max_batch), static_cast<cudaStream_t>(stream)));
   cudaEvent_t e0 = nullptr, e1 = nullptr;

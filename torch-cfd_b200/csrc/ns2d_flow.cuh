@@ -47,6 +47,7 @@ struct FlowParams {
   cx<typename pack2<T>::type>* w0U; // [W] unit-layout copy of the call's input state (dw/dt), or null
   int* sync;  // [0] ticket, [1] unused, [2 .. 2+B) rows counters, [2+B .. 2+2B) cols counters
   int* err;   // host-visible error word (0 = ok)
+  long long wait_cycles;  // bound of a dependency wait in SM cycles (0 = unbounded); TCFD_FLOW_TIMEOUT_S, default 3 s
   unsigned long long* prof;  // [16] cycles of thread 0 per region, summed over CTAs (profiling variant only)
 };
 
@@ -82,9 +83,10 @@ TCFD_D void flow_signal(int* p) {
   __atomic_fetch_add(p, 1, __ATOMIC_RELEASE);
 #endif
 }
-// one thread: wait until *p >= target.  A wait that exceeds ~3 s of SM clock is a lost dependency
-// (never a legitimate wait): the error word is raised and the grid is killed instead of hanging.
-TCFD_D void flow_wait(const int* p, int target, int* err) {
+// one thread: wait until *p >= target.  A wait that exceeds the bound (default ~3 s of SM clock; TCFD_FLOW_TIMEOUT_S,
+// 0 disables it for debuggers / sanitizers / time-sliced GPUs) is a lost dependency: the error word is raised and the
+// grid is killed instead of hanging.
+TCFD_D void flow_wait(const int* p, int target, int* err, long long wait_cycles) {
 #ifndef TCFD_EMU
   if (flow_ld_acquire(p) < target) {
     const long long t0 = clock64();
@@ -93,7 +95,7 @@ TCFD_D void flow_wait(const int* p, int target, int* err) {
       __nanosleep(ns);
       if (ns < 1024) ns *= 2;  // back off: hundreds of CTAs polling one word would starve the producers' REDs
       if (flow_ld_acquire(p) >= target) break;
-      if ((spin & 255u) == 0 && (*reinterpret_cast<volatile int*>(err) != 0 || clock64() - t0 > 6000000000ll)) {
+      if ((spin & 255u) == 0 && (*reinterpret_cast<volatile int*>(err) != 0 || (wait_cycles > 0 && clock64() - t0 > wait_cycles))) {
         *reinterpret_cast<volatile int*>(err) = 1;
         __threadfence_system();
         asm volatile("trap;");
@@ -220,7 +222,7 @@ TCFD_D cx<typename lane_traits<L>::scalar> lane_rt(cx<L> v, int lane) {
   do {                                \
     const int pr_ = prof_cur;         \
     FLOW_MARK(1);                     \
-    flow_wait(PTR, TGT, fp.err);      \
+    flow_wait(PTR, TGT, fp.err, fp.wait_cycles); \
     FLOW_MARK(pr_);                   \
   } while (0)
 // GR: double rows per rows item, GC: column quads per cols item (GC divides N/4).

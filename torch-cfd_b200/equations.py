@@ -369,6 +369,17 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         return vort_hat, 1 / (steps * dt) * (vort_hat - vort_old)
 
     @torch.no_grad()
+    def check_kernels(self, device=None):
+        """Raise if a kernel of an earlier (now synchronised) call on ``device`` reported a failure, e.g. the bounded
+        dependency wait of the dataflow launch (tcfd_ns2d_check; bound: TCFD_FLOW_TIMEOUT_S seconds, 0 disables it)."""
+        want = None
+        if device is not None:
+            d = torch.device(device)
+            want = d.index if d.index is not None else torch.cuda.current_device()
+        for key, plan in list(self._plans.items()):
+            if want is None or key == want:
+                plan.check()
+
     def forward_host(self, vort_hat_host: torch.Tensor, dt, steps=1, device=None, out=None, dvdt_out=None):
         """End-to-end variant for HOST-resident states: uploads the (preferably pinned) CPU
         tensor, steps on the GPU and downloads both results (tcfd_ns2d_step_host).  Returns pinned
@@ -391,6 +402,8 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
         if o.data_ptr() == w.data_ptr():
             raise ValueError("out must not alias the input")
         with torch.cuda.device(dev):
-            self._plan(dev, w.shape[0]).step(w, o, d, steps, beta, gdt, mu, 1 / (steps * dt), host=True)
+            plan = self._plan(dev, w.shape[0])
+            plan.step(w, o, d, steps, beta, gdt, mu, 1 / (steps * dt), host=True)
             torch.cuda.current_stream().synchronize()
+            plan.check()  # a kernel-side failure (dependency time-out of the dataflow launch) surfaces here, not later
         return o.view(shape), d.view(shape)

@@ -158,6 +158,8 @@ def get_trajectory_imex(equation, w0: torch.Tensor, dt: float, num_steps: int = 
     for k, v in snaps.items():
         v = v.reshape(*lead, v.shape[1], n, nh)
         out[k] = v if device_result else _to_host(v)
+    if not device_result and w0.is_cuda and hasattr(equation, "check_kernels"):
+        equation.check_kernels(w0.device)  # the copies above synchronised: surface a kernel-side failure here
     return out
 
 
