@@ -368,7 +368,6 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
             vort_hat = self.solver(vort_hat, dt, self)
         return vort_hat, 1 / (steps * dt) * (vort_hat - vort_old)
 
-    @torch.no_grad()
     def check_kernels(self, device=None):
         """Raise if a kernel of an earlier (now synchronised) call on ``device`` reported a failure, e.g. the bounded
         dependency wait of the dataflow launch (tcfd_ns2d_check; bound: TCFD_FLOW_TIMEOUT_S seconds, 0 disables it)."""
@@ -380,6 +379,7 @@ class NavierStokes2DSpectral(ImplicitExplicitODE):
             if want is None or key == want:
                 plan.check()
 
+    @torch.no_grad()
     def forward_host(self, vort_hat_host: torch.Tensor, dt, steps=1, device=None, out=None, dvdt_out=None):
         """End-to-end variant for HOST-resident states: uploads the (preferably pinned) CPU
         tensor, steps on the GPU and downloads both results (tcfd_ns2d_step_host).  Returns pinned
