@@ -136,10 +136,12 @@ ns2d_small_kernel(const FlowParams<T> fp) {
       const int y = valid ? col : N - 1;
       cx<T> a[1][8], b[1][8];
 #pragma unroll
-      for (int m = 0; m < 8; ++m) a[0][m] = Z1[(size_t)(t + m * NT) * ZS + y];
+      // (groups past the last column run the transforms for the group barriers only: they must not read a column another
+      // group is about to overwrite below)
+      for (int m = 0; m < 8; ++m) a[0][m] = valid ? Z1[(size_t)(t + m * NT) * ZS + y] : cx<T>{T(0), T(0)};
       fft_run<T, N, +1, 1, false, N>(a, tw, buf, parity, t, sync);
 #pragma unroll
-      for (int m = 0; m < 8; ++m) b[0][m] = Z2[(size_t)(t + m * NT) * ZS + y];
+      for (int m = 0; m < 8; ++m) b[0][m] = valid ? Z2[(size_t)(t + m * NT) * ZS + y] : cx<T>{T(0), T(0)};
       fft_run<T, N, +1, 1, false, N>(b, tw, buf, parity, t, sync);
       if (valid) {
 #pragma unroll
