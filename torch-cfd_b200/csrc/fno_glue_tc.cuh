@@ -291,11 +291,11 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
       for (int i = 0; i < CH; ++i) cv[i] = valid ? __ldcs(cp + (unsigned)i * stride) : 0.f;
 #pragma unroll
       for (int i = 0; i < CH; ++i) xv[i] = valid ? __ldcs(xp + (unsigned)i * stride) : 0.f;
-    } else {
+    } else {  // running pointers: one 64-bit add per access instead of a multiply and an add
 #pragma unroll
-      for (int i = 0; i < CH; ++i) cv[i] = __ldcs(cp + (unsigned)i * stride);
+      for (int i = 0; i < CH; ++i) { cv[i] = __ldcs(cp); cp += stride; }
 #pragma unroll
-      for (int i = 0; i < CH; ++i) xv[i] = __ldcs(xp + (unsigned)i * stride);
+      for (int i = 0; i < CH; ++i) { xv[i] = __ldcs(xp); xp += stride; }
     }
   };
 
@@ -346,7 +346,8 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         const float v = d[j] + b2r[j];
-        __stcs(yp + (unsigned)j * stride, act ? gelu_erf_tc(v) : v);
+        __stcs(yp, act ? gelu_erf_tc(v) : v);
+        yp += stride;
       }
     }
     // (the next tile's operand stores and products are ordered after this tile's tcgen05.ld by the barrier that
