@@ -121,7 +121,8 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned saddr, unsigned
 // 1 + erf): one reciprocal, one exponential, six fused multiply-adds instead of the ~30 instructions of erff --
 // the GELUs are the only arithmetic this kernel leaves on the CUDA cores, 2 C of them per point.
 //   gelu(v) = v/2 (1 + erf(v / sqrt 2)) = v/2 + |v|/2 (1 - poly(t) exp(-v^2/2)),  t = 1 / (1 + p |v| / sqrt 2)
-__device__ __forceinline__ float gelu_erf_tc(float v) {
+// The function returns 2 gelu(v) = v + |v| erf(|v| / sqrt 2).
+__device__ __forceinline__ float gelu2_erf_tc(float v) {
   const float av = fabsf(v);
   float t, ex;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(av, 0.3275911f * 0.70710678118654752440f, 1.0f)));  // argument in [1, inf)
@@ -132,7 +133,7 @@ __device__ __forceinline__ float gelu_erf_tc(float v) {
   pl *= t;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(av * av * (-0.5f * 1.4426950408889634f)));
   const float e = fmaf(-pl, ex, 1.0f);  // erf(|v| / sqrt 2)
-  return fmaf(0.5f * av, e, 0.5f * v);
+  return fmaf(av, e, v);                // = 2 gelu(v): the caller folds the factor 1/2 (into W2, or one multiply)
 }
 
 // n consecutive 32-bit columns of this thread's lane, in pieces of 8 / 4 / 2 / 1
@@ -325,7 +326,7 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
     float g[CH];
     tmem_ld<CH>(trow + COL_D + ch0, g);
 #pragma unroll
-    for (int j = 0; j < CH; ++j) g[j] = gelu_erf_tc(g[j] + b1r[j]);
+    for (int j = 0; j < CH; ++j) g[j] = gelu2_erf_tc(g[j] + b1r[j]);  // 2 gelu(h): W2's image carries the 1/2
     split_store(g, COL_A0);  // the first product is complete: its operand columns are free
     tmem_wait_st();
     fence_before();
@@ -346,7 +347,7 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         const float v = d[j] + b2r[j];
-        __stcs(yp, act ? gelu_erf_tc(v) : v);
+        __stcs(yp, act ? 0.5f * gelu2_erf_tc(v) : v);
         yp += stride;
       }
     }
@@ -365,7 +366,8 @@ TcWeights<KP> pack_tc(const float* w1, const float* b1, const float* w2, const f
   for (int m = 0; m < 3; ++m)
     for (int n = 0; n < NP; ++n)
       for (int k = 0; k < KP; ++k) {
-        const float v = (n < C && k < C) ? mats[m][n * C + k] : 0.f;  // torch Conv3d layout [out][in] = B[n][k]
+        // torch Conv3d layout [out][in] = B[n][k]; W2 (m = 1) is halved: the kernel feeds it 2 gelu(h) (exact scaling)
+        const float v = (n < C && k < C) ? (m == 1 ? 0.5f : 1.0f) * mats[m][n * C + k] : 0.f;
         uint32_t bits;
         memcpy(&bits, &v, 4);
         bits &= 0xFFFFE000u;
