@@ -213,7 +213,9 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
   __shared__ float b1s[NP], b2s[NP];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ unsigned tmem_slot;
-  const int t = threadIdx.x, warp = t >> 5;
+  // (the shuffle tells the compiler the warp index is warp-uniform: TMEM addresses are then formed on the uniform
+  // datapath instead of per lane + R2UR)
+  const int t = threadIdx.x, warp = __shfl_sync(0xffffffffu, t >> 5, 0);
   const int half = warp >> 2, pt = (warp & 3) * 32 + (t & 31);  // channel half, point of the tile
   const int ch0 = half * CH;
   {
@@ -228,7 +230,7 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
   fence_before();
   __syncthreads();
   fence_after();
-  const unsigned tbase = tmem_slot;
+  const unsigned tbase = __shfl_sync(0xffffffffu, tmem_slot, 0);
   const unsigned trow = tbase + ((unsigned)((warp & 3) * 32) << 16);  // this warp's 32 lanes
   const unsigned bbase = smem_addr(bimg);
   unsigned parity = 0;
@@ -344,11 +346,18 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
     tmem_ld<CH>(trow + COL_D + ch0, d);
     if (!TAIL || cur_valid) {
       float* yp = y + cur_off;
+      if (act) {  // (kernel-uniform: one branch per tile, not one select per channel)
 #pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        const float v = d[j] + b2r[j];
-        __stcs(yp, act ? 0.5f * gelu2_erf_tc(v) : v);
-        yp += stride;
+        for (int j = 0; j < CH; ++j) {
+          __stcs(yp, 0.5f * gelu2_erf_tc(d[j] + b2r[j]));
+          yp += stride;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          __stcs(yp, d[j] + b2r[j]);
+          yp += stride;
+        }
       }
     }
     // (the next tile's operand stores and products are ordered after this tile's tcgen05.ld by the barrier that
