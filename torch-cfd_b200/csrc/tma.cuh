@@ -70,24 +70,26 @@ TCFD_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-// Spin on the phase; bounded by the SM clock (about 2 s) so that a lost transaction traps instead of
-// hanging the GPU.
+// Wait for the phase.  try_wait suspends the warp for the hardware's default window; the retry loop is four
+// instructions and bounded by the retry count, so that a lost transaction traps instead of hanging the GPU (an earlier
+// version re-read the SM clock on every retry, which cost issue slots while other warps had work; an explicit 2 us
+// suspend-time hint doubled the time of the spectral-conv plane kernels at Y = 128: their waits are short and frequent).
+TCFD_D bool mbar_try_wait(unsigned addr, unsigned phase) {
+  unsigned done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(phase)
+      : "memory");
+  return done != 0;
+}
 TCFD_D void mbar_wait(unsigned long long* bar, unsigned phase) {
   const unsigned addr = smem_u32(bar);
-  unsigned done = 0;
-  long long t0 = 0;
-  for (unsigned spin = 0;; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(phase)
-        : "memory");
-    if (done) return;
-    if (spin == 64) t0 = clock64();
-    if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) asm volatile("trap;");
-  }
+  if (mbar_try_wait(addr, phase)) return;
+  for (unsigned spin = 0; !mbar_try_wait(addr, phase); ++spin)
+    if (spin > (1u << 26)) asm volatile("trap;");
 }
 TCFD_D void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
   asm volatile(
