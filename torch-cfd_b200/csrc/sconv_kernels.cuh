@@ -643,14 +643,20 @@ sconv_planes_inv3_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
   // staging of a spectrum block: even mt -- every thread copies 16-byte pieces into the padded rows (LDGSTS, completion
   // by wait_group + the group barrier); odd mt -- one contiguous bulk copy by thread 0 (mbarrier completion)
   const int upr = mt >> 1;  // 16-byte units per row (even mt)
+  const int rows_per_it = (upr > 0 && NT % upr == 0) ? NT / upr : 0, row0 = upr > 0 ? t / upr : 0, wi0 = upr > 0 ? t % upr : 0;
   auto stage_block = [&](int it) {
     int p = plane_of(it);
     if (p >= nplanes) p = nplanes - 1;
     const cx<float>* src = Z2 + (size_t)p * NKY * mt;
     if (rowcopy) {
-      for (int u = t; u < NKY * upr; u += NT) {
-        const int row = u / upr, wi = u - row * upr;
-        ldgsts16(zin + (size_t)row * ZS * 8 + wi * 16, reinterpret_cast<const unsigned char*>(src) + (size_t)u * 16);
+      if (rows_per_it > 0) {  // NT is a multiple of the units per row: (row, unit) advance without a division
+        for (int row = row0; row < NKY; row += rows_per_it)
+          ldgsts16(zin + (size_t)row * ZS * 8 + wi0 * 16, reinterpret_cast<const unsigned char*>(src) + ((size_t)row * upr + wi0) * 16);
+      } else {
+        for (int u = t; u < NKY * upr; u += NT) {
+          const int row = u / upr, wi = u - row * upr;
+          ldgsts16(zin + (size_t)row * ZS * 8 + wi * 16, reinterpret_cast<const unsigned char*>(src) + (size_t)u * 16);
+        }
       }
       ldgsts_commit();
     } else if (t == 0) {
