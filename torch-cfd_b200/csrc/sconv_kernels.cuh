@@ -376,7 +376,8 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
           v2 = (4 * q + 2 < T) ? r[2] : 0.f;
           v3 = (4 * q + 3 < T) ? r[3] : 0.f;
         }
-        z[0][m] = cx<f2>{f2(v0, v2), f2(v1, v3)};  // lane lo: x[t0] + i x[t0+1]; lane hi: x[t0+2] + i x[t0+3]
+        // lane lo: x[t0] + i x[t0+2]; lane hi: x[t0+1] + i x[t0+3] -- the two 8-byte loads ARE the packed operands (no repacking moves)
+        z[0][m] = cx<f2>{f2(v0, v1), f2(v2, v3)};
       }
       if (q == TQ - 1) {
         // the plane is in registers: the next one is staged under the rest of this plane's work
@@ -398,10 +399,10 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
         const f2 ar = 0.5f * (e.x + n.x), ai = 0.5f * (e.y - n.y);
         const f2 br = 0.5f * (e.y + n.y), bi = 0.5f * (n.x - e.x);
         cx<float>* o = Xy + (size_t)kyi * XS + 4 * q;
-        o[0] = cx<float>{ar.lo, ai.lo};
-        o[1] = cx<float>{br.lo, bi.lo};
-        o[2] = cx<float>{ar.hi, ai.hi};
-        o[3] = cx<float>{br.hi, bi.hi};
+        o[0] = cx<float>{ar.lo, ai.lo};  // t0     (real part of lane lo)
+        o[1] = cx<float>{ar.hi, ai.hi};  // t0 + 1 (real part of lane hi)
+        o[2] = cx<float>{br.lo, bi.lo};  // t0 + 2 (imaginary part of lane lo)
+        o[3] = cx<float>{br.hi, bi.hi};  // t0 + 3
       }
       sync();
     }
@@ -717,7 +718,9 @@ sconv_planes_inv3_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
           const cx<float> b = i2 >= 0 ? D[(size_t)i2 * XS + 4 * q + j] : cx<float>{0.f, 0.f};
           h[j] = cx<float>{0.5f * (a.x + b.x), 0.5f * (a.y - b.y)};
         }
-        Dh[e] = cx<f2>{f2(h[0].x - h[1].y, h[2].x - h[3].y), f2(h[0].y + h[1].x, h[2].y + h[3].x)};
+        // lane lo: h0 + i h2, lane hi: h1 + i h3 -- the transform then leaves (y[t0], y[t0+1]) and (y[t0+2], y[t0+3]) as its
+        // packed real and imaginary parts, stored without repacking
+        Dh[e] = cx<f2>{f2(h[0].x - h[2].y, h[1].x - h[3].y), f2(h[0].y + h[2].x, h[1].y + h[3].x)};
       }
       sync();
       cx<f2> z[8];
@@ -726,12 +729,12 @@ sconv_planes_inv3_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
       for (int m = 0; m < 8; ++m) {
         float* r = tile + (t + m * NT) * T + 4 * q;
         if (teven) {
-          *reinterpret_cast<cx<float>*>(r) = cx<float>{z[m].x.lo, z[m].y.lo};
-          if (4 * q + 2 < T) *reinterpret_cast<cx<float>*>(r + 2) = cx<float>{z[m].x.hi, z[m].y.hi};
+          *reinterpret_cast<f2*>(r) = z[m].x;
+          if (4 * q + 2 < T) *reinterpret_cast<f2*>(r + 2) = z[m].y;
         } else {
           r[0] = z[m].x.lo;
-          if (4 * q + 1 < T) r[1] = z[m].y.lo;
-          if (4 * q + 2 < T) r[2] = z[m].x.hi;
+          if (4 * q + 1 < T) r[1] = z[m].x.hi;
+          if (4 * q + 2 < T) r[2] = z[m].y.lo;
           if (4 * q + 3 < T) r[3] = z[m].y.hi;
         }
       }
