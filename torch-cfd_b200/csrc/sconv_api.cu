@@ -147,7 +147,14 @@ int launch_planes_inv3(const cplx* Z2, float* y, const cplx* Sy, const cplx* tw,
   const size_t smem = S::table_bytes(d.Tout, d.mt) + S::GP * S::group_bytes(d.Tout, d.my, d.mt);
   if (smem > 227 * 1024 || (reinterpret_cast<uintptr_t>(y) & 15u) || (reinterpret_cast<uintptr_t>(Z2) & 15u))
     return launch_planes_inv2<Y>(Z2, y, Sy, tw, d, nplanes, st);
-  auto k = sconv_planes_inv3_kernel<Y, MYT>;
+  if (d.my == MYT) {  // every twiddle of the instantiation is used: the variant without bound checks
+    auto k = sconv_planes_inv3_kernel<Y, MYT, true>;
+    if (int rc = set_smem(k, smem)) return rc;
+    const int grid = planes_grid(reinterpret_cast<const void*>(k), S::GP * S::NT, smem, (nplanes + S::GP - 1) / S::GP);
+    TCFD_LAUNCH(k, grid, S::GP * S::NT, smem, st, Z2, y, Sy, tw, d, nplanes);
+    return 0;
+  }
+  auto k = sconv_planes_inv3_kernel<Y, MYT, false>;
   if (int rc = set_smem(k, smem)) return rc;
   const int grid = planes_grid(reinterpret_cast<const void*>(k), S::GP * S::NT, smem, (nplanes + S::GP - 1) / S::GP);
   TCFD_LAUNCH(k, grid, S::GP * S::NT, smem, st, Z2, y, Sy, tw, d, nplanes);
