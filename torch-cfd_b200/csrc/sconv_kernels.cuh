@@ -385,11 +385,18 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
         if (t == 0 && it + 1 < iters) issue(it + 1);
       }
       fft_run<f2, Y, -1, 1, false, Y>(z, tw, buf, parity, t, sync);
+      if (my < NT) {
+        // (group-uniform) only the first and the last register row hold kept frequencies: two predicated stores instead of
+        // sixteen divergent tests, and the other outputs of the closing pass are dead code
+        if (t <= my) Es[t] = z[0][0];
+        if (t >= NT - my) Es[2 * my + 1 + t - NT] = z[0][7];
+      } else {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int ky = t + m * NT;
-        if (ky <= my) Es[ky] = z[0][m];
-        else if (ky >= Y - my) Es[my + 1 + ky - (Y - my)] = z[0][m];
+        for (int m = 0; m < 8; ++m) {
+          const int ky = t + m * NT;
+          if (ky <= my) Es[ky] = z[0][m];
+          else if (ky >= Y - my) Es[my + 1 + ky - (Y - my)] = z[0][m];
+        }
       }
       sync();
       for (int kyi = t; kyi < NKY; kyi += NT) {
@@ -903,11 +910,18 @@ sconv_xaxis_fwd2_kernel(const cx<float>* __restrict__ in, cx<float>* __restrict_
     const int pair = (tile_id % ntx) * GP + g;
     if (pair < npairs) {
       cx<float>* dst = out + (size_t)(tile_id / ntx) * NKX * ncol + 2 * pair;
+      auto put = [&](int kxi, const cx<f2>& v) {  // both columns of the pair in one 16-byte store
+        *reinterpret_cast<cx<f2>*>(dst + (size_t)kxi * ncol) = cx<f2>{f2(v.x.lo, v.y.lo), f2(v.x.hi, v.y.hi)};
+      };
+      if (mx <= NT) {  // (uniform) kept rows live in the first and the last register row only
+        if (t < mx) put(t, z[0][0]);
+        if (t >= NT - mx) put(2 * mx + t - NT, z[0][7]);
+      } else {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int kxi = kept_index(t + m * NT, X, mx);
-        if (kxi >= 0)  // both columns of the pair in one 16-byte store
-          *reinterpret_cast<cx<f2>*>(dst + (size_t)kxi * ncol) = cx<f2>{f2(z[0][m].x.lo, z[0][m].y.lo), f2(z[0][m].x.hi, z[0][m].y.hi)};
+        for (int m = 0; m < 8; ++m) {
+          const int kxi = kept_index(t + m * NT, X, mx);
+          if (kxi >= 0) put(kxi, z[0][m]);
+        }
       }
     }
     cur ^= 1;
