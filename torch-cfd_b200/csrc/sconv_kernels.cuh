@@ -339,6 +339,7 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
   // thread mapping of the register-tiled t-axis product (one division per kernel, none per plane)
   const int NP = (mt + 1) / 2, KL = NT / (NP > 0 ? NP : 1), pl = t % NP, kl = t / NP;
   const bool tiled = NP <= NT;
+  const int rk1 = tiled ? (NKY + KL - 1) / KL : 0;
   for (int i = threadIdx.x; i < mt * T; i += blockDim.x) As[(i / T) * AS + i % T] = A[i];
   const int stride = (int)gridDim.x * GP;
   const int iters = (nplanes + stride - 1) / stride;
@@ -417,8 +418,11 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
       cx<float>* dst = Z1 + (size_t)plane * NKY * mt;
       if (tiled) {
         // t-axis analysis: Z1[kyi][kt] = sum_tt A[kt][tt] Xy[kyi][tt], register-tiled (group_cproduct)
-        group_cproduct<4>(As, AS, Xy, XS, NKY, mt, T, pl, kl, KL, kl < KL,
-                          [&](int kyi, int kt, cx<float> v) { dst[(size_t)kyi * mt + kt] = v; });
+        // rows per thread so that ONE pass covers the NKY rows when that takes at most 7 (C4: 40 rows / 8 = 5)
+        auto put = [&](int kyi, int kt, cx<float> v) { dst[(size_t)kyi * mt + kt] = v; };
+        if (rk1 == 5) group_cproduct<5>(As, AS, Xy, XS, NKY, mt, T, pl, kl, KL, kl < KL, put);
+        else if (rk1 == 6 || rk1 == 7) group_cproduct<7>(As, AS, Xy, XS, NKY, mt, T, pl, kl, KL, kl < KL, put);
+        else group_cproduct<4>(As, AS, Xy, XS, NKY, mt, T, pl, kl, KL, kl < KL, put);
       } else {
         for (int j = t; j < NKY * mt; j += NT) {
           const int kyi = j / mt, kt = j % mt;
@@ -650,6 +654,7 @@ sconv_planes_inv3_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
   const bool rowcopy = (mt & 1) == 0;
   const int NP = (T + 1) / 2, KL = NT / (NP > 0 ? NP : 1), pl = t % NP, kl = t / NP;
   const bool tiled = NP <= NT;
+  const int rk1 = tiled ? (NKY + KL - 1) / KL : 0;  // rows per thread for a single pass of the t-axis product
   for (int i = threadIdx.x; i < mt * T; i += blockDim.x) Ss[(i / mt) * SS + i % mt] = Sy[i];
   const int stride = (int)gridDim.x * GP;
   const int iters = (nplanes + stride - 1) / stride;
@@ -693,8 +698,10 @@ sconv_planes_inv3_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
     }
     const cx<float>* src = reinterpret_cast<const cx<float>*>(zin);
     if (tiled) {
-      group_cproduct<4>(Ss, SS, src, ZS, NKY, T, mt, pl, kl, KL, kl < KL,
-                        [&](int kyi, int tt, cx<float> v) { D[(size_t)kyi * XS + tt] = v; });
+      auto put = [&](int kyi, int tt, cx<float> v) { D[(size_t)kyi * XS + tt] = v; };
+      if (rk1 == 5) group_cproduct<5>(Ss, SS, src, ZS, NKY, T, mt, pl, kl, KL, kl < KL, put);
+      else if (rk1 == 6 || rk1 == 7) group_cproduct<7>(Ss, SS, src, ZS, NKY, T, mt, pl, kl, KL, kl < KL, put);
+      else group_cproduct<4>(Ss, SS, src, ZS, NKY, T, mt, pl, kl, KL, kl < KL, put);
       if (T < TQ * 4)
         for (int kyi = t; kyi < NKY; kyi += NT)
           for (int tt = T; tt < TQ * 4; ++tt) D[(size_t)kyi * XS + tt] = cx<float>{0.f, 0.f};
