@@ -400,17 +400,29 @@ sconv_planes_fwd2_kernel(const float* __restrict__ x, cx<float>* __restrict__ Z1
         }
       }
       sync();
-      for (int kyi = t; kyi < NKY; kyi += NT) {
-        const int ky = kept_freq(kyi, Y, my), kn = (Y - ky) % Y;
-        const cx<f2> e = Es[ky <= my ? ky : my + 1 + ky - (Y - my)];
+      // separation of the two real transforms of each lane, one mirror pair (ky = p, Y - p) per thread: both outputs
+      // come from the same two entries and are complex conjugates of each other (a single pass over p = 0..my)
+      for (int p = t; p <= my; p += NT) {
+        const cx<f2> e = Es[p];
+        const int kn = (Y - p) % Y;  // (kn == my only when my = Y/2: that frequency then has a single entry, Es[my])
         const cx<f2> n = Es[kn <= my ? kn : my + 1 + kn - (Y - my)];
+        // X_a = (E(k) + conj E(-k)) / 2 ;  X_b = (E(k) - conj E(-k)) / (2i)
         const f2 ar = 0.5f * (e.x + n.x), ai = 0.5f * (e.y - n.y);
         const f2 br = 0.5f * (e.y + n.y), bi = 0.5f * (n.x - e.x);
-        cx<float>* o = Xy + (size_t)kyi * XS + 4 * q;
-        o[0] = cx<float>{ar.lo, ai.lo};  // t0     (real part of lane lo)
-        o[1] = cx<float>{ar.hi, ai.hi};  // t0 + 1 (real part of lane hi)
-        o[2] = cx<float>{br.lo, bi.lo};  // t0 + 2 (imaginary part of lane lo)
-        o[3] = cx<float>{br.hi, bi.hi};  // t0 + 3
+        if (p < my) {  // ky = p (ky = my is not a kept output, only the partner of Y - my)
+          cx<float>* o = Xy + (size_t)p * XS + 4 * q;
+          o[0] = cx<float>{ar.lo, ai.lo};  // t0     (real part of lane lo)
+          o[1] = cx<float>{ar.hi, ai.hi};  // t0 + 1 (real part of lane hi)
+          o[2] = cx<float>{br.lo, bi.lo};  // t0 + 2 (imaginary part of lane lo)
+          o[3] = cx<float>{br.hi, bi.hi};  // t0 + 3
+        }
+        if (p > 0) {  // ky = Y - p, kept index 2 my - p: the conjugates
+          cx<float>* o = Xy + (size_t)(2 * my - p) * XS + 4 * q;
+          o[0] = cx<float>{ar.lo, -ai.lo};
+          o[1] = cx<float>{ar.hi, -ai.hi};
+          o[2] = cx<float>{br.lo, -bi.lo};
+          o[3] = cx<float>{br.hi, -bi.hi};
+        }
       }
       sync();
     }
@@ -727,11 +739,11 @@ sconv_planes_inv3_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
     for (int q = 0; q < TQ; ++q) {
       cx<f2>* Dh = Dh0;
       if (q > 0) sync();  // the previous quad's reads of Dh
-      for (int e = t; e < 2 * my + 1; e += NT) {
-        const int ky = e <= my ? e : Y - my + (e - my - 1);
-        const int kn = (Y - ky) % Y;
-        int i1 = kept_index(ky, Y, my), i2 = kept_index(kn, Y, my);
-        i1 = i1 >= 0 ? i1 : NKY;  // the zero row
+      // Hermitian part along ky, one mirror pair (ky = p, Y - p) per thread: the two packed entries come from the same
+      // eight loads (the mirror's time samples are the complex conjugates); a single pass over p = 0..my
+      for (int p = t; p <= my; p += NT) {
+        int i1 = kept_index(p, Y, my), i2 = kept_index((Y - p) % Y, Y, my);
+        i1 = i1 >= 0 ? i1 : NKY;  // the zero row (ky = my is not a kept input)
         i2 = i2 >= 0 ? i2 : NKY;
         cx<float> h[4];
 #pragma unroll
@@ -742,7 +754,9 @@ sconv_planes_inv3_kernel(const cx<float>* __restrict__ Z2, float* __restrict__ y
         }
         // lane lo: h0 + i h2, lane hi: h1 + i h3 -- the transform then leaves (y[t0], y[t0+1]) and (y[t0+2], y[t0+3]) as its
         // packed real and imaginary parts, stored without repacking
-        Dh[e] = cx<f2>{f2(h[0].x - h[2].y, h[1].x - h[3].y), f2(h[0].y + h[2].x, h[1].y + h[3].x)};
+        Dh[p] = cx<f2>{f2(h[0].x - h[2].y, h[1].x - h[3].y), f2(h[0].y + h[2].x, h[1].y + h[3].x)};
+        if (p > 0)  // entry of ky = Y - p: conj(h0) + i conj(h2), conj(h1) + i conj(h3)
+          Dh[2 * my + 1 - p] = cx<f2>{f2(h[0].x + h[2].y, h[1].x + h[3].y), f2(h[2].x - h[0].y, h[3].x - h[1].y)};
       }
       sync();
       cx<f2> z[8];
