@@ -238,16 +238,25 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
   const unsigned trow = tbase + ((unsigned)((warp & 3) * 32) << 16);  // this warp's 32 lanes
   const unsigned bbase = smem_addr(bimg);
   unsigned parity = 0;
-  if constexpr (KP > C) {  // K padding columns of the four operand blocks: zero for the life of the CTA
+  // KP > C: the K padding columns of the four operand blocks are written once for the life of the CTA -- zero, except the
+  // first padding column of the hi block of operand A0, which is ONE: the matching rows of the W1 / W2 images hold the
+  // biases (b1; b2 + bw), so the tensor core adds them (no per-channel bias registers or adds on the CUDA cores)
+  constexpr bool BIAS_MMA = KP > C;
+  if constexpr (KP > C) {
     if (half == 0) {
-      const float z[KP - C] = {};
+      float z[KP - C] = {};
 #pragma unroll
-      for (int blk = 0; blk < 4; ++blk) tmem_st<KP - C>(trow + COL_A0 + blk * KP + C, z);
+      for (int blk = 0; blk < 4; ++blk) {
+        z[0] = blk == 0 ? 1.0f : 0.0f;
+        tmem_st<KP - C>(trow + COL_A0 + blk * KP + C, z);
+      }
     }
   }
-  float b1r[CH], b2r[CH];
+  float b1r[BIAS_MMA ? 1 : CH], b2r[BIAS_MMA ? 1 : CH];
+  if constexpr (!BIAS_MMA) {
 #pragma unroll
-  for (int j = 0; j < CH; ++j) { b1r[j] = b1s[ch0 + j]; b2r[j] = b2s[ch0 + j]; }
+    for (int j = 0; j < CH; ++j) { b1r[j] = b1s[ch0 + j]; b2r[j] = b2s[ch0 + j]; }
+  }
 
   auto split_store = [&](const float (&v)[CH], unsigned col) {  // hi -> col + ch0 .., lo -> col + KP + ch0 ..
     float hi[CH], lo[CH];
@@ -332,7 +341,7 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
     float g[CH];
     tmem_ld<CH>(trow + COL_D + ch0, g);
 #pragma unroll
-    for (int j = 0; j < CH; ++j) g[j] = gelu2_erf_tc(g[j] + b1r[j]);  // 2 gelu(h): W2's image carries the 1/2
+    for (int j = 0; j < CH; ++j) g[j] = gelu2_erf_tc(BIAS_MMA ? g[j] : g[j] + b1r[j]);  // 2 gelu(h): W2's image carries the 1/2
     split_store(g, COL_A0);  // the first product is complete: its operand columns are free
     tmem_wait_st();
     fence_before();
@@ -353,13 +362,13 @@ fno_layer_glue_tc_kernel(const float* __restrict__ c, const float* __restrict__ 
       if (act) {  // (kernel-uniform: one branch per tile, not one select per channel)
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          __stcs(yp, 0.5f * gelu2_erf_tc(d[j] + b2r[j]));
+          __stcs(yp, 0.5f * gelu2_erf_tc(BIAS_MMA ? d[j] : d[j] + b2r[j]));
           yp += stride;
         }
       } else {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          __stcs(yp, d[j] + b2r[j]);
+          __stcs(yp, BIAS_MMA ? d[j] : d[j] + b2r[j]);
           yp += stride;
         }
       }
@@ -392,6 +401,19 @@ TcWeights<KP> pack_tc(const float* w1, const float* b1, const float* w2, const f
   for (int n = 0; n < NP; ++n) {
     W.b1[n] = (b1 && n < C) ? b1[n] : 0.f;
     W.b2[n] = n < C ? (b2 ? b2[n] : 0.f) + (bw ? bw[n] : 0.f) : 0.f;
+  }
+  if (KP > C) {  // the kernel's operand A0 carries a constant 1 in K column C: that column of W1 / W2 is the bias
+    for (int m = 0; m < 2; ++m)
+      for (int n = 0; n < NP; ++n) {
+        const float v = m == 0 ? W.b1[n] : W.b2[n];
+        uint32_t bits;
+        memcpy(&bits, &v, 4);
+        bits &= 0xFFFFE000u;
+        float hi;
+        memcpy(&hi, &bits, 4);
+        W.img[2 * m][C / 4][n / 8][n % 8][C % 4] = hi;
+        W.img[2 * m + 1][C / 4][n / 8][n % 8][C % 4] = v - hi;
+      }
   }
   return W;
 }
