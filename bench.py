@@ -488,8 +488,9 @@ def run_sconv(a):
 
     def fwdbwd():
         y = m(x)
+        plan_launches[0] += sum(p.last_launch_count for p in m._cache._plans.values())  # the forward call (5 kernels)
         y.backward(cot)
-        plan_launches[0] += sum(p.last_launch_count for p in m._cache._plans.values())
+        plan_launches[0] += sum(p.last_launch_count for p in m._cache._plans.values())  # the backward call (6 kernels)
         x.grad = None
         for p in m.parameters():
             p.grad = None
