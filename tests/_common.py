@@ -68,11 +68,17 @@ class default_dtype:
         torch.set_default_dtype(self.prev)
 
 
+_EMU_CHECKED = False
+
+
 def ensure_emu_lib():
-    """Build tests/emu/libtcfd_emu.so (plain g++, the kernels compiled for host threads) if absent."""
-    if not os.path.exists(EMU_LIB):
+    """Build tests/emu/libtcfd_emu.so (plain g++, the kernels compiled for host threads) if absent OR older than the
+    kernel sources (one `make emu` per test process: a no-op when up to date, so a stale library is never tested)."""
+    global _EMU_CHECKED
+    if not _EMU_CHECKED or not os.path.exists(EMU_LIB):
         subprocess.run(["make", "-C", CSRC, "-j", str(min(8, os.cpu_count() or 1)), "emu"], check=True,
                        stdout=subprocess.DEVNULL)
+        _EMU_CHECKED = True
     return EMU_LIB
 
 
